@@ -1,0 +1,325 @@
+"""ctypes binding of the C ABI in include/pbf_b200.h (libpbf_b200.so).
+
+Python here is plumbing for tests and bench.py only: the product is the shared
+library plus the C++ host layer in fluidsimulator_b200/csrc/host.  There is no CPU
+fallback — if the library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libpbf_b200.so"
+
+PBF_MODE_STRICT = 0
+PBF_MODE_FAST = 1
+
+SCRATCH_IDS = {
+    "pred_x": 0, "pred_y": 1, "pred_z": 2,
+    "delta_x": 3, "delta_y": 4, "delta_z": 5,
+    "lambda": 6, "rho": 7,
+    "dv_x": 8, "dv_y": 9, "dv_z": 10,
+    "omega_x": 11, "omega_y": 12, "omega_z": 13, "omega_mag": 14,
+    "eta_x": 15, "eta_y": 16, "eta_z": 17,
+}
+
+STAGES = ["predict", "sort", "cells", "neighbors", "lambda", "delta", "xsph",
+          "vort_omega", "vort_apply", "finalize", "exchange"]
+
+PBF_COMM_ID_BYTES = 128
+
+
+class PbfParams(C.Structure):
+    """POD mirror of fluid::Params (reference core/include/fluid/core.h:11-43)."""
+
+    _fields_ = [
+        ("dt", C.c_float),
+        ("density", C.c_float),
+        ("particle_mass", C.c_float),
+        ("h", C.c_float),
+        ("particle_radius", C.c_float),
+        ("epsilon", C.c_float),
+        ("solver_iterations", C.c_int32),
+        ("neighbor_reserve_factor", C.c_float),
+        ("use_uniform_grid", C.c_int32),
+        ("enable_scorr", C.c_int32),
+        ("enable_xsph", C.c_int32),
+        ("enable_vorticity", C.c_int32),
+        ("scorr_k", C.c_float),
+        ("scorr_n", C.c_int32),
+        ("scorr_dq_coeff", C.c_float),
+        ("visc_c", C.c_float),
+        ("plane_restitution", C.c_float),
+        ("plane_friction", C.c_float),
+        ("vort_epsilon", C.c_float),
+        ("vort_norm_eps", C.c_float),
+        ("external_force", C.c_float * 3),
+    ]
+
+    @staticmethod
+    def defaults() -> "PbfParams":
+        """fluid::Params defaults (core.h:12-43)."""
+        p = PbfParams()
+        p.dt = np.float32(1.0) / np.float32(60.0)
+        p.density = 6000.0
+        p.particle_mass = 0.0
+        p.h = 0.0
+        p.particle_radius = 0.01
+        p.epsilon = 600.0
+        p.solver_iterations = 4
+        p.neighbor_reserve_factor = 1.5
+        p.use_uniform_grid = 1
+        p.enable_scorr = 0
+        p.enable_xsph = 0
+        p.enable_vorticity = 0
+        p.scorr_k = 0.00005
+        p.scorr_n = 4
+        p.scorr_dq_coeff = 0.3
+        p.visc_c = 0.0002
+        p.plane_restitution = 0.0
+        p.plane_friction = 0.0
+        p.vort_epsilon = 0.5
+        p.vort_norm_eps = 1e-6
+        p.external_force[0] = 0.0
+        p.external_force[1] = -9.8
+        p.external_force[2] = 0.0
+        return p
+
+    def copy(self) -> "PbfParams":
+        q = PbfParams()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(PbfParams))
+        return q
+
+    def as_dict(self) -> dict:
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if name == "external_force" else v
+        return out
+
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+def fptr(a):
+    """float32 C-contiguous numpy array -> float* (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_f32p)
+
+
+def iptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_i32p)
+
+
+# every symbol include/pbf_b200.h declares: name -> (restype, argtypes)
+ABI = {
+    "pbf_default_params": (None, [C.POINTER(PbfParams)]),
+    "pbf_abi_version": (C.c_int, []),
+    "pbf_device_count": (C.c_int, [C.POINTER(C.c_char_p)]),
+    "pbf_create": (C.c_void_p, [C.c_int, C.c_size_t]),
+    "pbf_destroy": (None, [C.c_void_p]),
+    "pbf_last_error": (C.c_char_p, [C.c_void_p]),
+    "pbf_set_params": (C.c_int, [C.c_void_p, C.POINTER(PbfParams)]),
+    "pbf_set_planes": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p]),
+    "pbf_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pbf_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
+    "pbf_download": (C.c_int, [C.c_void_p] + [_f32p] * 6),
+    "pbf_step": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_step_host": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6 + [C.c_int]),
+    "pbf_count": (C.c_size_t, [C.c_void_p]),
+    "pbf_time": (C.c_float, [C.c_void_p]),
+    "pbf_set_time": (C.c_int, [C.c_void_p, C.c_float]),
+    "pbf_debug_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "pbf_debug_grid": (C.c_int, [C.c_void_p] + [_i32p] * 7),
+    "pbf_debug_neighbors": (C.c_int, [C.c_void_p, _i32p, _i32p]),
+    "pbf_debug_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_debug_scratch": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
+    "pbf_stage_name": (C.c_char_p, [C.c_int]),
+    "pbf_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_profile_reset": (C.c_int, [C.c_void_p]),
+    "pbf_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "pbf_launch_count": (C.c_uint64, [C.c_void_p]),
+    "pbf_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "pbf_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pbf_slab_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
+    "pbf_slab_owned": (C.c_size_t, [C.c_void_p]),
+    "pbf_slab_download": (C.c_int, [C.c_void_p, _i64p] + [_f32p] * 6),
+}
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    """dlopen libpbf_b200.so and type every exported entry point.  Raises if the
+    library or any declared symbol is missing (there is no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise RuntimeError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C fluidsimulator_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+    for name, (restype, argtypes) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class PbfError(RuntimeError):
+    pass
+
+
+class Solver:
+    """Thin object wrapper over one pbf_ctx (one GPU / one slab)."""
+
+    def __init__(self, device: int = 0, capacity: int = 0, mode: int = PBF_MODE_STRICT):
+        self.lib = load_library()
+        self.ctx = self.lib.pbf_create(device, capacity)
+        if not self.ctx:
+            msg = self.lib.pbf_last_error(None)
+            raise PbfError((msg or b"pbf_create failed").decode())
+        self._check(self.lib.pbf_set_mode(self.ctx, mode))
+        self.n = 0
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.pbf_last_error(self.ctx)
+            raise PbfError(f"pbf error {rc}: {(msg or b'?').decode()}")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pbf_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -----------------------------------------------------
+    def set_params(self, params: PbfParams):
+        self._check(self.lib.pbf_set_params(self.ctx, C.byref(params)))
+
+    def set_planes(self, planes: np.ndarray):
+        """planes: float32 [P,4] rows (nx, ny, nz, d)."""
+        planes = np.ascontiguousarray(planes, dtype=np.float32).reshape(-1, 4)
+        cols = [np.ascontiguousarray(planes[:, k]) for k in range(4)]
+        self._check(self.lib.pbf_set_planes(self.ctx, planes.shape[0], *[fptr(c) for c in cols]))
+
+    def set_mode(self, mode: int):
+        self._check(self.lib.pbf_set_mode(self.ctx, mode))
+
+    def set_stream(self, stream_ptr: int | None):
+        self._check(self.lib.pbf_set_stream(self.ctx, C.c_void_p(stream_ptr or 0)))
+
+    def set_graph(self, enabled: bool):
+        self._check(self.lib.pbf_set_graph(self.ctx, int(enabled)))
+
+    # -- state ---------------------------------------------------------------
+    def upload(self, state6):
+        """state6: six float32 arrays (pos x,y,z, vel x,y,z) in original order."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in state6]
+        n = arrs[0].shape[0]
+        self._check(self.lib.pbf_upload(self.ctx, n, *[fptr(a) for a in arrs]))
+        self.n = n
+
+    def download(self):
+        n = int(self.lib.pbf_count(self.ctx))
+        out = [np.empty(n, dtype=np.float32) for _ in range(6)]
+        self._check(self.lib.pbf_download(self.ctx, *[fptr(a) for a in out]))
+        return out
+
+    def step(self, nsteps: int = 1):
+        self._check(self.lib.pbf_step(self.ctx, nsteps))
+
+    def step_host(self, state6, nsteps: int = 1):
+        """The cuda_step contract: host arrays in/out (modified in place)."""
+        n = state6[0].shape[0]
+        self._check(self.lib.pbf_step_host(self.ctx, n, *[fptr(a) for a in state6], nsteps))
+        self.n = n
+
+    @property
+    def time(self) -> float:
+        return float(self.lib.pbf_time(self.ctx))
+
+    def set_time(self, t: float):
+        self._check(self.lib.pbf_set_time(self.ctx, t))
+
+    def count(self) -> int:
+        return int(self.lib.pbf_count(self.ctx))
+
+    # -- parity surface ------------------------------------------------------
+    def debug_enable(self, on: bool = True):
+        self._check(self.lib.pbf_debug_enable(self.ctx, int(on)))
+
+    def debug_sizes(self):
+        nc, nn = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.pbf_debug_sizes(self.ctx, C.byref(nc), C.byref(nn)))
+        return int(nc.value), int(nn.value)
+
+    def debug_grid(self):
+        n = self.count()
+        nc, _ = self.debug_sizes()
+        ecx, ecy, ecz, ep = (np.empty(n, dtype=np.int32) for _ in range(4))
+        cxyz = np.empty(3 * nc, dtype=np.int32)
+        cs, ce = (np.empty(nc, dtype=np.int32) for _ in range(2))
+        self._check(self.lib.pbf_debug_grid(self.ctx, iptr(ecx), iptr(ecy), iptr(ecz), iptr(ep),
+                                            iptr(cxyz), iptr(cs), iptr(ce)))
+        return {"entry_cx": ecx, "entry_cy": ecy, "entry_cz": ecz, "entry_particle": ep,
+                "cell_xyz": cxyz.reshape(-1, 3), "cell_start": cs, "cell_end": ce}
+
+    def debug_neighbors(self):
+        n = self.count()
+        _, nn = self.debug_sizes()
+        prefix = np.empty(n, dtype=np.int32)
+        idx = np.empty(max(nn, 1), dtype=np.int32)
+        self._check(self.lib.pbf_debug_neighbors(self.ctx, iptr(prefix), iptr(idx)))
+        return prefix, idx[:nn]
+
+    def debug_scratch(self, name: str) -> np.ndarray:
+        out = np.empty(self.count(), dtype=np.float32)
+        self._check(self.lib.pbf_debug_scratch(self.ctx, SCRATCH_IDS[name], fptr(out)))
+        return out
+
+    # -- measurement ---------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.pbf_profile_enable(self.ctx, int(on)))
+
+    def profile_reset(self):
+        self._check(self.lib.pbf_profile_reset(self.ctx))
+
+    def profile(self) -> dict:
+        out = {}
+        for k, name in enumerate(STAGES):
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            self._check(self.lib.pbf_profile_get(self.ctx, k, C.byref(ms), C.byref(cnt)))
+            out[name] = {"ms": ms.value, "launches": int(cnt.value)}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.pbf_launch_count(self.ctx))
+
+
+def device_count() -> int:
+    lib = load_library()
+    err = C.c_char_p()
+    return int(lib.pbf_device_count(C.byref(err)))

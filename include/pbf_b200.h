@@ -1,0 +1,210 @@
+/*
+ * pbf_b200.h — C ABI of the B200-native Position-Based-Fluids substep backend.
+ *
+ * This is the drop-in boundary for the one hot path of CTKnight/FluidSimulator:
+ * the PBF substep.  The reference exposes that path as three C++ free functions
+ * (reference cuda/include/fluid/cuda.h:7-9):
+ *
+ *     int  fluid::cuda_version();
+ *     bool fluid::cuda_device_available(int* count, const char** error);
+ *     void fluid::cuda_step(const Params& params, State& state);
+ *
+ * called from exactly one site (reference app/src/main.cpp:171-187 probe,
+ * :250-254 step).  Everything below is plain C: pointers, sizes and PODs.
+ * The C++ shim that re-creates the three reference symbols on top of this ABI
+ * lives in fluidsimulator_b200/csrc/host/cuda_shim.cpp; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returning int returns PBF_OK (0) or a negative PBF_E_* code;
+ *     the human-readable reason is available from pbf_last_error().
+ *   - there is NO CPU fallback: without a usable CUDA device pbf_create() fails.
+ *   - particle arrays are SoA float32 in ORIGINAL particle order, exactly like
+ *     fluid::State (reference core/include/fluid/core.h:121-132).
+ */
+#ifndef PBF_B200_H
+#define PBF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBF_ABI_VERSION 1
+
+/* status codes */
+#define PBF_OK 0
+#define PBF_E_INVALID (-1)   /* bad argument / bad state                       */
+#define PBF_E_CUDA (-2)      /* a CUDA runtime call failed                     */
+#define PBF_E_NODEVICE (-3)  /* no CUDA device                                 */
+#define PBF_E_CAPACITY (-4)  /* a device table could not be grown              */
+#define PBF_E_COMM (-5)      /* NCCL / slab exchange failure                   */
+
+/* arithmetic modes (pbf_set_mode) */
+#define PBF_MODE_STRICT 0 /* IEEE binary32, oracle operation order, no FMA contraction:
+                             bit-identical to the reference CPU path (core.cpp:119-615) */
+#define PBF_MODE_FAST 1   /* FMA contraction + approximate sqrt; tolerance-gated        */
+
+/* POD mirror of fluid::Params (reference core/include/fluid/core.h:11-79),
+ * minus `backend` (meaningless here) and the plane arrays (pbf_set_planes). */
+typedef struct pbf_params {
+  float dt;                      /* core.h:12 */
+  float density;                 /* core.h:18 */
+  float particle_mass;           /* core.h:20 */
+  float h;                       /* core.h:22 */
+  float particle_radius;         /* core.h:23 (unused by the substep) */
+  float epsilon;                 /* core.h:24 */
+  int32_t solver_iterations;     /* core.h:25 */
+  float neighbor_reserve_factor; /* core.h:26 (host-vector hint; ignored) */
+  int32_t use_uniform_grid;      /* core.h:27 (must be non-zero; the O(N^2) path is out of scope) */
+  int32_t enable_scorr;          /* core.h:28 */
+  int32_t enable_xsph;           /* core.h:29 */
+  int32_t enable_vorticity;      /* core.h:30 */
+  float scorr_k;                 /* core.h:31 */
+  int32_t scorr_n;               /* core.h:32 */
+  float scorr_dq_coeff;          /* core.h:33 */
+  float visc_c;                  /* core.h:34 */
+  float plane_restitution;       /* core.h:35 */
+  float plane_friction;          /* core.h:36 */
+  float vort_epsilon;            /* core.h:37 */
+  float vort_norm_eps;           /* core.h:38 */
+  float external_force[3];       /* core.h:39-43 */
+} pbf_params;
+
+/* Fills *p with the defaults of fluid::Params (core.h:12-43). */
+void pbf_default_params(pbf_params* p);
+
+typedef struct pbf_ctx pbf_ctx;
+
+int pbf_abi_version(void);
+
+/* Replaces fluid::cuda_device_available (reference cuda_stub.cu:740-762).
+ * Returns the device count (>= 0) or a negative code; *err (if non-NULL) gets a
+ * borrowed static string or NULL. */
+int pbf_device_count(const char** err);
+
+/* One context = one GPU = one slab of particles.  `capacity` is a particle-count
+ * hint (tables grow on demand).  Returns NULL on failure (see pbf_last_error(NULL)). */
+pbf_ctx* pbf_create(int device, size_t capacity);
+void pbf_destroy(pbf_ctx* ctx);
+
+/* Borrowed string, valid until the next failing call on the same ctx.
+ * ctx == NULL reports the last context-less failure (pbf_create, pbf_device_count). */
+const char* pbf_last_error(const pbf_ctx* ctx);
+
+int pbf_set_params(pbf_ctx* ctx, const pbf_params* params);
+/* Plane SoA, reference core.h:44-78; normals are used as given (already normalised). */
+int pbf_set_planes(pbf_ctx* ctx, int count, const float* nx, const float* ny,
+                   const float* nz, const float* d);
+int pbf_set_mode(pbf_ctx* ctx, int mode);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) so that the
+ * caller's CUDA events bracket the work.  NULL = the context's own stream. */
+int pbf_set_stream(pbf_ctx* ctx, void* cuda_stream);
+/* 1 = replay each substep as a CUDA graph (default), 0 = plain stream launches. */
+int pbf_set_graph(pbf_ctx* ctx, int enabled);
+
+/* Host SoA -> device (the six H2D copies of reference cuda_stub.cu:791-796).
+ * Resets nothing else; time is kept (use pbf_set_time). */
+int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py,
+               const float* pz, const float* vx, const float* vy, const float* vz);
+/* Device -> host SoA in original particle order (reference cuda_stub.cu:1092-1097).
+ * Any pointer may be NULL to skip that array. */
+int pbf_download(pbf_ctx* ctx, float* px, float* py, float* pz, float* vx,
+                 float* vy, float* vz);
+
+/* Runs `nsteps` substeps (reference core.cpp:119-615 each) device-resident:
+ * no host<->device particle traffic, no host synchronisation between substeps.
+ * Synchronises the stream before returning and validates the device tables
+ * (a substep that overflowed a table is re-run after growing it; the result is
+ * independent of table sizes). */
+int pbf_step(pbf_ctx* ctx, int nsteps);
+
+/* The reference's cuda_step contract in one call (cuda_stub.cu:764-1099): host
+ * arrays in, `nsteps` substeps, host arrays out, all inside the call. */
+int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz,
+                  float* vx, float* vy, float* vz, int nsteps);
+
+size_t pbf_count(const pbf_ctx* ctx);
+float pbf_time(const pbf_ctx* ctx);       /* State::time, float-accumulated (core.cpp:614) */
+int pbf_set_time(pbf_ctx* ctx, float t);
+
+/* ---- parity / debug surface (mirrors what fluid::step leaves in State::cpu,
+ * reference core.h:92-115).  All refer to the LAST substep executed. ---------- */
+
+/* Occupied-cell count and total neighbour-list length of the last substep. */
+int pbf_debug_sizes(pbf_ctx* ctx, size_t* ncells, size_t* nneighbors);
+/* grid_entries (core.h:112): per sorted slot the cell coordinates and particle id;
+ * grid_keys/grid_starts/grid_ends (core.h:113-115): per occupied cell.
+ * Arrays: entry_* [n]; cell_xyz [3*ncells] (x,y,z interleaved); cell_start/end [ncells]. */
+int pbf_debug_grid(pbf_ctx* ctx, int32_t* entry_cx, int32_t* entry_cy,
+                   int32_t* entry_cz, int32_t* entry_particle, int32_t* cell_xyz,
+                   int32_t* cell_start, int32_t* cell_end);
+/* neighbor_prefix_sum (inclusive, per ORIGINAL particle id) and neighbor_indices
+ * (original ids, oracle traversal order) — core.h:110-111, core.cpp:205-247. */
+int pbf_debug_neighbors(pbf_ctx* ctx, int32_t* prefix_sum, int32_t* indices);
+
+/* Per-particle float scratch in original order (core.h:92-109). */
+enum pbf_scratch_id {
+  PBF_SCRATCH_PRED_X = 0, PBF_SCRATCH_PRED_Y, PBF_SCRATCH_PRED_Z,
+  PBF_SCRATCH_DELTA_X, PBF_SCRATCH_DELTA_Y, PBF_SCRATCH_DELTA_Z,
+  PBF_SCRATCH_LAMBDA, PBF_SCRATCH_RHO,
+  PBF_SCRATCH_DV_X, PBF_SCRATCH_DV_Y, PBF_SCRATCH_DV_Z,
+  PBF_SCRATCH_OMEGA_X, PBF_SCRATCH_OMEGA_Y, PBF_SCRATCH_OMEGA_Z, PBF_SCRATCH_OMEGA_MAG,
+  PBF_SCRATCH_ETA_X, PBF_SCRATCH_ETA_Y, PBF_SCRATCH_ETA_Z,
+  PBF_SCRATCH_COUNT
+};
+/* Enables retention of the scratch arrays (extra stores in the kernels). */
+int pbf_debug_enable(pbf_ctx* ctx, int enabled);
+int pbf_debug_scratch(pbf_ctx* ctx, int scratch_id, float* out);
+
+/* ---- measurement surface ------------------------------------------------- */
+
+enum pbf_stage_id {
+  PBF_STAGE_PREDICT = 0, /* a3+a4: integrate, cell coordinates, bounds          */
+  PBF_STAGE_SORT,        /* a5: radix sort by cell key                           */
+  PBF_STAGE_CELLS,       /* a6: cell start/end table + reorder into sorted order */
+  PBF_STAGE_NEIGHBORS,   /* a7: neighbour list                                   */
+  PBF_STAGE_LAMBDA,      /* a8                                                   */
+  PBF_STAGE_DELTA,       /* a9+a10 (+a11 on the last iteration)                  */
+  PBF_STAGE_XSPH,        /* a12                                                  */
+  PBF_STAGE_VORT_OMEGA,  /* a13 first pass                                       */
+  PBF_STAGE_VORT_APPLY,  /* a13 second pass + apply                              */
+  PBF_STAGE_FINALIZE,    /* a14 + scatter back to original order                 */
+  PBF_STAGE_EXCHANGE,    /* slab halo / migration traffic (multi-GPU only)       */
+  PBF_STAGE_COUNT
+};
+const char* pbf_stage_name(int stage);
+/* With profiling on, substeps are launched un-graphed with CUDA events around
+ * every stage; totals accumulate until pbf_profile_reset. */
+int pbf_profile_enable(pbf_ctx* ctx, int enabled);
+int pbf_profile_reset(pbf_ctx* ctx);
+int pbf_profile_get(pbf_ctx* ctx, int stage, double* total_ms, uint64_t* launches);
+/* Number of this library's kernels launched since creation (graph replays counted
+ * by the kernels they contain). */
+uint64_t pbf_launch_count(const pbf_ctx* ctx);
+
+/* ---- slab decomposition (one ctx per rank; x-slabs) ------------ */
+
+/* Size in bytes of the opaque id produced by pbf_comm_unique_id. */
+#define PBF_COMM_ID_BYTES 128
+/* Rank 0 calls this and ships the bytes to every rank by any host channel
+ * (torch.distributed broadcast, a file, MPI...). */
+int pbf_comm_unique_id(void* id_bytes);
+/* Joins the NCCL communicator of `nranks` slabs.  Collective. */
+int pbf_comm_init(pbf_ctx* ctx, int rank, int nranks, const void* id_bytes);
+/* Distributes a global particle set: every rank passes the SAME global arrays and
+ * keeps the particles of its x-slab (cuts on cell boundaries, equal counts).
+ * Global original ids are retained for gathering. */
+int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float* py,
+                    const float* pz, const float* vx, const float* vy, const float* vz);
+/* Number of particles currently owned by this slab, and their global ids. */
+size_t pbf_slab_owned(const pbf_ctx* ctx);
+int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py,
+                      float* pz, float* vx, float* vy, float* vz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBF_B200_H */
