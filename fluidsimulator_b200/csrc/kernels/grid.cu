@@ -1,0 +1,428 @@
+// grid.cu — neighbour-grid kernels of the PBF substep for sm_100a:
+//   a3  predict / integrate            (reference core/src/core.cpp:150-161)
+//   a4  cell coordinates and keys      (core.cpp:28-34, 164-171)
+//   a5  sort by (x, y, z, particle id) (core.cpp:12-21, 173-183)  -> stable LSD radix sort
+//   a6  cell start/end table           (core.cpp:185-203)         -> dense bbox-relative table
+//   a7  neighbour list                 (core.cpp:205-247)         -> warp-interleaved ELL list
+//
+// Integer results (keys, sorted order, cell table, neighbour sets) are bit-exact with
+// the reference in BOTH arithmetic modes: everything that feeds them uses explicit
+// round-to-nearest intrinsics, never contracted.
+//
+// Key design points
+//   * dense key = ((x-x0)*ny + (y-y0))*nz + (z-z0) over the per-substep bounding box of
+//     occupied cells: order-isomorphic to the reference's lexicographic (x,y,z) compare,
+//     so a STABLE sort of particles presented in id order reproduces the reference's
+//     (key, particle) total order exactly, with ~20 key bits => 3 radix passes.
+//   * the table is (start,end) per dense cell, padded by one empty layer so the 27-cell
+//     stencil needs no bounds checks.
+//   * nothing here synchronises with the host: bounds, cell counts and overflow flags
+//     live in device memory (GridDesc / StatusBlock).
+#include "pbf_kernels.h"
+
+namespace pbf {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ bool batch_failed(const StatusBlock* st) {
+  return (st->grid_overflow | st->nbr_overflow) != 0;
+}
+
+// ---------------------------------------------------------------- state (de)interleave
+__global__ void __launch_bounds__(kThreads)
+k_pack_state(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
+             const float* __restrict__ vx, const float* __restrict__ vy, const float* __restrict__ vz,
+             float4* __restrict__ pos_o, float4* __restrict__ vel_o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos_o[i] = make_float4(px[i], py[i], pz[i], 0.0f);
+  vel_o[i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_unpack_state(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
+               float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz,
+               float* __restrict__ vx, float* __restrict__ vy, float* __restrict__ vz, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pos_o[i];
+  const float4 v = vel_o[i];
+  if (px) px[i] = p.x;
+  if (py) py[i] = p.y;
+  if (pz) pz[i] = p.z;
+  if (vx) vx[i] = v.x;
+  if (vy) vy[i] = v.y;
+  if (vz) vz[i] = v.z;
+}
+
+// ---------------------------------------------------------------- a3 + a4 bounds
+// vel += g*dt; pred = pos + vel*dt (core.cpp:155-160), then min/max of the cell
+// coordinates.  Grid-stride so that only a few thousand warps touch the six atomics.
+__global__ void __launch_bounds__(kThreads)
+k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
+          float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, int n) {
+  if (batch_failed(st)) return;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX};
+  int hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pos_o[i];
+    const float4 v = vel_o[i];
+    const float vx = __fadd_rn(v.x, c.gdt_x);
+    const float vy = __fadd_rn(v.y, c.gdt_y);
+    const float vz = __fadd_rn(v.z, c.gdt_z);
+    const float qx = __fadd_rn(p.x, __fmul_rn(vx, c.dt));
+    const float qy = __fadd_rn(p.y, __fmul_rn(vy, c.dt));
+    const float qz = __fadd_rn(p.z, __fmul_rn(vz, c.dt));
+    pred_o[i] = make_float4(qx, qy, qz, 0.0f);
+    const int cx = cell_coord(qx, c.inv_h), cy = cell_coord(qy, c.inv_h), cz = cell_coord(qz, c.inv_h);
+    lo[0] = min(lo[0], cx); hi[0] = max(hi[0], cx);
+    lo[1] = min(lo[1], cy); hi[1] = max(hi[1], cy);
+    lo[2] = min(lo[2], cz); hi[2] = max(hi[2], cz);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int wlo = __reduce_min_sync(0xffffffffu, lo[a]);
+    const int whi = __reduce_max_sync(0xffffffffu, hi[a]);
+    if ((threadIdx.x & 31) == 0) {
+      // plain loads first: after the first few warps almost nobody needs the atomic
+      if (wlo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], wlo);
+      if (whi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], whi);
+    }
+  }
+}
+
+// One thread: bounds -> GridDesc, capacity check, reset of the running bounds.
+__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap) {
+  if (batch_failed(st)) return;
+  unsigned long long cells = 1;
+  bool bad = false;
+  for (int a = 0; a < 3; ++a) {
+    const long long lo = (long long)st->min_cell[a] - 1;
+    const long long hi = (long long)st->max_cell[a] + 1;
+    const long long dim = hi - lo + 1;
+    if (st->min_cell[a] == INT_MIN || st->max_cell[a] == INT_MIN || dim <= 0 || dim > 0x7fffffffLL) bad = true;
+    desc->lo[a] = (int)lo;
+    desc->hi[a] = (int)hi;
+    desc->dim[a] = (int)dim;
+    if (!bad) {
+      if (cells > 0xffffffffffffULL / (unsigned long long)dim) bad = true; else cells *= (unsigned long long)dim;
+    }
+    st->min_cell[a] = INT_MAX;
+    st->max_cell[a] = INT_MIN;
+  }
+  if (bad) cells = 0xffffffffffffULL;
+  if (cells > st->max_cells) st->max_cells = cells;
+  const int overflow = (cells > (unsigned long long)cell_cap) ? 1 : 0;
+  desc->ncells = overflow ? 0u : (uint32_t)cells;
+  desc->overflow = overflow;
+  if (overflow) st->grid_overflow = 1;
+}
+
+// ---------------------------------------------------------------- a4/a5 keys + radix sort
+__device__ __forceinline__ uint32_t dense_key(float4 q, float inv_h, const GridDesc& d) {
+  const int cx = cell_coord(q.x, inv_h) - d.lo[0];
+  const int cy = cell_coord(q.y, inv_h) - d.lo[1];
+  const int cz = cell_coord(q.z, inv_h) - d.lo[2];
+  return ((uint32_t)cx * (uint32_t)d.dim[1] + (uint32_t)cy) * (uint32_t)d.dim[2] + (uint32_t)cz;
+}
+
+// keys in ORIGINAL particle order + the per-block digit histogram of radix pass 0.
+__global__ void __launch_bounds__(kThreads)
+k_keys_hist(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist,
+            float inv_h, const GridDesc* __restrict__ desc, const StatusBlock* st, int n, int nblocks) {
+  __shared__ uint32_t sh[kRadixBins];
+  if (batch_failed(st)) return;
+  const GridDesc d = *desc;
+  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) sh[b] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortTile / kThreads; ++r) {
+    const int i = base + r * kThreads + threadIdx.x;
+    if (i < n) {
+      const uint32_t k = dense_key(pred_o[i], inv_h, d);
+      keys[i] = k;
+      atomicAdd(&sh[k & (kRadixBins - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) hist[b * nblocks + blockIdx.x] = sh[b];
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_radix_hist(const uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, const StatusBlock* st,
+             int n, int nblocks, int shift) {
+  __shared__ uint32_t sh[kRadixBins];
+  if (batch_failed(st)) return;
+  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) sh[b] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortTile / kThreads; ++r) {
+    const int i = base + r * kThreads + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) hist[b * nblocks + blockIdx.x] = sh[b];
+}
+
+// Exclusive scan of hist[digit*nblocks + block] (one block; m = 256*nblocks is small).
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+k_radix_scan(uint32_t* __restrict__ hist, const StatusBlock* st, int m) {
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  __shared__ uint32_t carry_sh;
+  if (batch_failed(st)) return;
+  if (threadIdx.x == 0) carry_sh = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // coalesced tiles of 4 elements per thread
+  for (int base = 0; base < m; base += kScanThreads * 4) {
+    const int i0 = base + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < m) ? hist[i0 + k] : 0u;
+    const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - w;  // exclusive over warps
+    }
+    __syncthreads();
+    const uint32_t carry = carry_sh;
+    uint32_t excl = carry + warp_sums[warp] + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < m) hist[i0 + k] = excl;
+      excl += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == kScanThreads - 1) carry_sh = excl;  // total so far
+    __syncthreads();
+  }
+}
+
+// Stable scatter of one radix pass.  Tile order is (warp, round, lane) == memory order;
+// ranks come from __match_any_sync peer groups plus per-warp digit counters.
+__global__ void __launch_bounds__(kThreads)
+k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                const uint32_t* __restrict__ offsets, const StatusBlock* st, int n, int nblocks, int shift) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kRounds = kSortTile / kThreads;  // per warp: kRounds x 32 consecutive keys
+  __shared__ uint32_t whist[kWarps][kRadixBins];
+  if (batch_failed(st)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = threadIdx.x; b < kWarps * kRadixBins; b += kThreads) (&whist[0][0])[b] = 0;
+  __syncthreads();
+
+  const int warp_base = blockIdx.x * kSortTile + warp * (kRounds * 32);
+  uint32_t key[kRounds], val[kRounds], rank[kRounds];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int i = warp_base + r * 32 + lane;
+    const bool valid = i < n;
+    key[r] = valid ? keys_in[i] : 0u;
+    val[r] = valid ? (vals_in ? vals_in[i] : (uint32_t)i) : 0u;
+    const uint32_t d = valid ? ((key[r] >> shift) & (kRadixBins - 1)) : (uint32_t)kRadixBins;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t below = __popc(peers & lt_mask);
+    const uint32_t prev = valid ? whist[warp][d] : 0u;
+    __syncwarp();
+    if (valid && below == 0) whist[warp][d] = prev + __popc(peers);
+    __syncwarp();
+    rank[r] = prev + below;
+  }
+  __syncthreads();
+  // per digit: global base of this block, then exclusive scan over the warps
+  for (int d = threadIdx.x; d < kRadixBins; d += kThreads) {
+    uint32_t running = offsets[d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t cnt = whist[w][d];
+      whist[w][d] = running;
+      running += cnt;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int i = warp_base + r * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (key[r] >> shift) & (kRadixBins - 1);
+      const uint32_t pos = whist[warp][d] + rank[r];
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- a6 cell table + reorder
+__global__ void __launch_bounds__(kThreads)
+k_clear_cells(int2* __restrict__ cell_range, const GridDesc* __restrict__ desc, const StatusBlock* st) {
+  if (batch_failed(st)) return;
+  const uint32_t ncells = desc->ncells;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x)
+    cell_range[c] = make_int2(0, 0);
+}
+
+// Sorted slot i: run boundaries -> cell_range (core.cpp:185-203), and gather of the
+// predicted / committed positions into sorted order (the reorder of north_star).
+__global__ void __launch_bounds__(kThreads)
+k_cells_reorder(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                const float4* __restrict__ pred_o, const float4* __restrict__ pos_o,
+                float4* __restrict__ pred_s, float4* __restrict__ pos_s,
+                int2* __restrict__ cell_range, const StatusBlock* st, int n) {
+  if (batch_failed(st)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  const uint32_t o = vals[i];
+  if (i == 0 || keys[i - 1] != k) cell_range[k].x = i;
+  if (i == n - 1 || keys[i + 1] != k) cell_range[k].y = i + 1;
+  const float4 q = pred_o[o];
+  const float4 p = pos_o[o];
+  pred_s[i] = make_float4(q.x, q.y, q.z, 0.0f);
+  pos_s[i] = make_float4(p.x, p.y, p.z, __uint_as_float(o));
+}
+
+// ---------------------------------------------------------------- a7 neighbour list
+// Thread per sorted particle; candidates in the reference order: dz, dy, dx with dx
+// innermost (core.cpp:211-213), ascending slot (== ascending particle id) inside a cell.
+// Entry k of particle i lives at idx[(i/32)*K*32 + k*32 + i%32]: the k-th load of a
+// warp in the solver passes is one coalesced 128-byte line.
+__global__ void __launch_bounds__(128)
+k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
+            const GridDesc* __restrict__ desc, uint32_t* __restrict__ nbr_idx,
+            uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2, int K, int n) {
+  if (batch_failed(st)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cnt = 0;
+  if (i < n) {
+    const float4 pi = pred_s[i];
+    const int dimy = desc->dim[1], dimz = desc->dim[2];
+    const int cx = cell_coord(pi.x, inv_h) - desc->lo[0];
+    const int cy = cell_coord(pi.y, inv_h) - desc->lo[1];
+    const int cz = cell_coord(pi.z, inv_h) - desc->lo[2];
+    uint32_t* out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31);
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy) {
+        const uint32_t row = ((uint32_t)(cx - 1) * (uint32_t)dimy + (uint32_t)(cy + dy)) * (uint32_t)dimz +
+                             (uint32_t)(cz + dz);
+        const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int2 range = cell_range[row + (uint32_t)dx * xstride];
+          for (int j = range.x; j < range.y; ++j) {
+            if (j == i) continue;
+            const float4 pj = pred_s[j];
+            const float ddx = __fsub_rn(pi.x, pj.x);
+            const float ddy = __fsub_rn(pi.y, pj.y);
+            const float ddz = __fsub_rn(pi.z, pj.z);
+            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+            if (r2 < h2) {  // core.cpp:238
+              if (cnt < (uint32_t)K) out[(size_t)cnt * 32u] = (uint32_t)j;
+              ++cnt;
+            }
+          }
+        }
+      }
+    nbr_count[i] = cnt < (uint32_t)K ? cnt : (uint32_t)K;
+  }
+  // batch statistics: max count (to size K) and the total (debug)
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, cnt);
+  const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) {
+    if (wmax > *(volatile unsigned int*)&st->max_neighbors) atomicMax(&st->max_neighbors, wmax);
+    if (wmax > (uint32_t)K) st->nbr_overflow = 1;
+    atomicAdd(&st->total_neighbors, (unsigned long long)wsum);
+  }
+}
+
+__global__ void k_begin_substep(StatusBlock* st) { st->total_neighbors = 0; }
+
+inline int grid_for(int n, int threads) { return (n + threads - 1) / threads; }
+
+}  // namespace
+
+// ================================================================== launchers
+int launch_pack_state(const float* const soa[6], float4* pos_o, float4* vel_o, int n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  k_pack_state<<<grid_for(n, kThreads), kThreads, 0, s>>>(soa[0], soa[1], soa[2], soa[3], soa[4], soa[5],
+                                                         pos_o, vel_o, n);
+  return 1;
+}
+
+int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const soa[6], int n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  k_unpack_state<<<grid_for(n, kThreads), kThreads, 0, s>>>(pos_o, vel_o, soa[0], soa[1], soa[2], soa[3],
+                                                           soa[4], soa[5], n);
+  return 1;
+}
+
+int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConsts& c,
+                   const GridBuffers& g, int n, cudaStream_t s) {
+  int blocks = grid_for(n, kThreads);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_begin_substep<<<1, 1, 0, s>>>(g.status);
+  k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n);
+  k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap);
+  return 3;
+}
+
+int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, int n, int* out,
+                cudaStream_t s) {
+  const int nblocks = sort_blocks(n);
+  const int m = kRadixBins * nblocks;
+  int launches = 0;
+  int cur = 0;
+  for (int pass = 0; pass < g.sort_passes; ++pass) {
+    const int shift = pass * kRadixBits;
+    if (pass == 0)
+      k_keys_hist<<<nblocks, kThreads, 0, s>>>(pred_o, g.keys[0], g.hist, c.inv_h, g.desc, g.status, n, nblocks);
+    else
+      k_radix_hist<<<nblocks, kThreads, 0, s>>>(g.keys[cur], g.hist, g.status, n, nblocks, shift);
+    k_radix_scan<<<1, kScanThreads, 0, s>>>(g.hist, g.status, m);
+    k_radix_scatter<<<nblocks, kThreads, 0, s>>>(g.keys[cur], pass == 0 ? nullptr : g.vals[cur],
+                                                g.keys[cur ^ 1], g.vals[cur ^ 1], g.hist, g.status, n,
+                                                nblocks, shift);
+    cur ^= 1;
+    launches += 3;
+  }
+  *out = cur;
+  return launches;
+}
+
+int launch_cells_reorder(const uint32_t* keys, const uint32_t* vals, const float4* pred_o,
+                         const float4* pos_o, float4* pred_s, float4* pos_s, const GridBuffers& g,
+                         int n, cudaStream_t s) {
+  k_clear_cells<<<148 * 4, kThreads, 0, s>>>(g.cell_range, g.desc, g.status);
+  k_cells_reorder<<<grid_for(n, kThreads), kThreads, 0, s>>>(keys, vals, pred_o, pos_o, pred_s, pos_s,
+                                                            g.cell_range, g.status, n);
+  return 2;
+}
+
+int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,
+                     const NeighborList& nl, int n, cudaStream_t s) {
+  k_neighbors<<<grid_for(n, 128), 128, 0, s>>>(pred_s, g.cell_range, g.desc, nl.idx, nl.count, g.status,
+                                              c.inv_h, c.h2, nl.K, n);
+  return 1;
+}
+
+}  // namespace pbf

@@ -1,0 +1,729 @@
+// pbf_capi.cu — the C ABI of include/pbf_b200.h: context management, the device-resident
+// substep driver (stream launches or a replayed CUDA graph), overflow-safe batching, and the
+// parity / measurement surfaces.  No CPU fallback exists anywhere in this file: every entry
+// point either runs the CUDA path or fails with an error string.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pbf_context.h"
+
+using namespace pbf;
+
+namespace {
+
+thread_local std::string g_error;  // context-less failures (pbf_create, pbf_device_count)
+
+int fail(pbf_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->error = msg; else g_error = msg;
+  return code;
+}
+
+#define PBF_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(ctx, PBF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+constexpr float kPi = 3.14159265358979323846f;  // core.cpp:10
+
+// poly6_kernel on the host, same float expression order as core.cpp:35-46
+float host_poly6(float r2, float h) {
+  const float h2 = h * h;
+  if (r2 > h2) return 0.0f;
+  const float diff = h2 - r2;
+  const float diff3 = diff * diff * diff;
+  const float h4 = h2 * h2;
+  const float h9 = h4 * h4 * h;
+  const float coeff = 315.0f / (64.0f * kPi * h9);
+  return coeff * diff3;
+}
+
+// Per-step constants in the oracle's float expression order (core.cpp:138-148, 270-274,
+// and the coefficient expressions inside poly6_kernel / spiky_gradient_factor).
+StepConsts make_consts(const pbf_params& p, int nplanes) {
+  StepConsts c{};
+  c.dt = p.dt;
+  c.inv_dt = 1.0f / p.dt;
+  const float h = p.h;
+  c.h = h;
+  c.h2 = h * h;
+  c.inv_h = 1.0f / h;
+  const float min_r = 0.01f * h;
+  c.min_r2 = min_r * min_r;
+  const float h2 = h * h;
+  const float h4 = h2 * h2;
+  const float h9 = h4 * h4 * h;
+  c.poly6_coeff = 315.0f / (64.0f * kPi * h9);
+  c.poly6_zero = host_poly6(0.0f, h);
+  const float h6 = h2 * h2 * h2;
+  c.spiky_coeff = -45.0f / (kPi * h6);
+  c.inv_density = 1.0f / p.density;
+  c.mass = p.particle_mass;
+  c.grad_scale = p.particle_mass * c.inv_density;
+  c.epsilon = p.epsilon;
+  const bool scorr_enabled = p.enable_scorr && p.scorr_k != 0.0f;
+  const float dq_coeff = (p.scorr_dq_coeff > 0.0f) ? p.scorr_dq_coeff : 0.3f;
+  const float scorr_dq = dq_coeff * h;
+  const float wdq = scorr_enabled ? host_poly6(scorr_dq * scorr_dq, h) : 0.0f;
+  c.scorr_inv_wdq = (wdq > 1e-12f) ? (1.0f / wdq) : 0.0f;
+  c.scorr_on = (scorr_enabled && c.scorr_inv_wdq > 0.0f) ? 1 : 0;
+  c.scorr_negk = -p.scorr_k;
+  c.scorr_n = p.scorr_n;
+  c.visc_c = p.visc_c;
+  c.vort_eps = p.vort_epsilon;
+  c.vort_norm_eps = p.vort_norm_eps;
+  c.restitution = p.plane_restitution;
+  c.one_minus_friction = 1.0f - p.plane_friction;
+  c.gdt_x = p.external_force[0] * p.dt;
+  c.gdt_y = p.external_force[1] * p.dt;
+  c.gdt_z = p.external_force[2] * p.dt;
+  c.nplanes = nplanes;
+  c.do_xsph = (p.enable_xsph && p.visc_c != 0.0f) ? 1 : 0;
+  c.do_vort = (p.enable_vorticity && p.vort_epsilon != 0.0f) ? 1 : 0;
+  c.do_rest = ((p.plane_restitution > 0.0f || p.plane_friction > 0.0f) && nplanes > 0) ? 1 : 0;
+  return c;
+}
+
+int sort_passes_for(uint32_t cell_cap) {
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < (unsigned long long)cell_cap) ++bits;
+  return (bits + kRadixBits - 1) / kRadixBits;
+}
+
+void invalidate_graph(pbf_ctx* ctx) {
+  if (ctx->graph_exec) {
+    cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr;
+  }
+}
+
+int ensure_particles(pbf_ctx* ctx, size_t n) {
+  if (n <= ctx->cap) return PBF_OK;
+  const size_t cap = std::max<size_t>(n, 1024);
+  invalidate_graph(ctx);
+  PBF_CUDA(ctx, ctx->pos_o.reserve(cap));
+  PBF_CUDA(ctx, ctx->vel_o.reserve(cap));
+  PBF_CUDA(ctx, ctx->pos_bak.reserve(cap));
+  PBF_CUDA(ctx, ctx->vel_bak.reserve(cap));
+  PBF_CUDA(ctx, ctx->pred_o.reserve(cap));
+  PBF_CUDA(ctx, ctx->pred_a.reserve(cap));
+  PBF_CUDA(ctx, ctx->pred_b.reserve(cap));
+  PBF_CUDA(ctx, ctx->pos_s.reserve(cap));
+  PBF_CUDA(ctx, ctx->vel_a.reserve(cap));
+  PBF_CUDA(ctx, ctx->vel_b.reserve(cap));
+  PBF_CUDA(ctx, ctx->omega.reserve(cap));
+  PBF_CUDA(ctx, ctx->rho.reserve(cap));
+  PBF_CUDA(ctx, ctx->keys0.reserve(cap));
+  PBF_CUDA(ctx, ctx->keys1.reserve(cap));
+  PBF_CUDA(ctx, ctx->vals0.reserve(cap));
+  PBF_CUDA(ctx, ctx->vals1.reserve(cap));
+  PBF_CUDA(ctx, ctx->hist.reserve((size_t)kRadixBins * sort_blocks((int)cap)));
+  PBF_CUDA(ctx, ctx->nbr_count.reserve(cap));
+  for (auto& b : ctx->soa) PBF_CUDA(ctx, b.reserve(cap));
+  ctx->cap = cap;
+  return PBF_OK;
+}
+
+int ensure_tables(pbf_ctx* ctx) {
+  if (ctx->cell_range.n < ctx->cell_cap) {
+    invalidate_graph(ctx);
+    PBF_CUDA(ctx, ctx->cell_range.reserve(ctx->cell_cap));
+  }
+  const size_t need = ((ctx->cap + 31) / 32) * (size_t)ctx->K * 32u;
+  if (ctx->nbr_idx.n < need) {
+    invalidate_graph(ctx);
+    PBF_CUDA(ctx, ctx->nbr_idx.reserve(need));
+  }
+  if (ctx->debug) {
+    PBF_CUDA(ctx, ctx->dbg_lambda.reserve(ctx->cap));
+    PBF_CUDA(ctx, ctx->dbg_rho.reserve(ctx->cap));
+    PBF_CUDA(ctx, ctx->dbg_delta.reserve(ctx->cap));
+    PBF_CUDA(ctx, ctx->dbg_dv.reserve(ctx->cap));
+    PBF_CUDA(ctx, ctx->dbg_eta.reserve(ctx->cap));
+  }
+  return PBF_OK;
+}
+
+// ---- stage profiling --------------------------------------------------------
+cudaEvent_t timer_event(StageTimer& t) {
+  if (!t.pool.empty()) {
+    cudaEvent_t e = t.pool.back();
+    t.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct StageCtx {
+  pbf_ctx* ctx;
+};
+
+void stage_mark(void* user, int stage, int begin) {
+  pbf_ctx* ctx = static_cast<pbf_ctx*>(user);
+  if (!ctx->profile) return;
+  StageTimer& t = ctx->timer;
+  cudaEvent_t e = timer_event(t);
+  cudaEventRecord(e, ctx->stream);
+  if (begin) {
+    t.begin.push_back(e);
+    t.stage.push_back(stage);
+  } else {
+    t.end.push_back(e);
+  }
+}
+
+void timer_resolve(pbf_ctx* ctx) {
+  StageTimer& t = ctx->timer;
+  for (size_t k = 0; k < t.end.size(); ++k) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, t.begin[k], t.end[k]) == cudaSuccess) t.total_ms[t.stage[k]] += ms;
+    t.pool.push_back(t.begin[k]);
+    t.pool.push_back(t.end[k]);
+  }
+  t.begin.clear();
+  t.end.clear();
+  t.stage.clear();
+}
+
+// ---- one substep ------------------------------------------------------------
+// Enqueues the kernels of one substep.  Returns the kernel count.
+int enqueue_substep(pbf_ctx* ctx) {
+  const int n = (int)ctx->n;
+  cudaStream_t s = ctx->stream;
+  GridBuffers g{};
+  g.desc = ctx->desc.p;
+  g.status = ctx->status.p;
+  g.keys[0] = ctx->keys0.p;
+  g.keys[1] = ctx->keys1.p;
+  g.vals[0] = ctx->vals0.p;
+  g.vals[1] = ctx->vals1.p;
+  g.hist = ctx->hist.p;
+  g.cell_range = ctx->cell_range.p;
+  g.cell_cap = ctx->cell_cap;
+  g.sort_passes = sort_passes_for(ctx->cell_cap);
+  NeighborList nl{ctx->nbr_idx.p, ctx->nbr_count.p, ctx->K};
+  const StepConsts& c = ctx->consts;
+  StageTimer& t = ctx->timer;
+  int launches = 0, k;
+
+  stage_mark(ctx, PBF_STAGE_PREDICT, 1);
+  k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n, s);
+  stage_mark(ctx, PBF_STAGE_PREDICT, 0);
+  t.launches[PBF_STAGE_PREDICT] += k; launches += k;
+
+  int out = 0;
+  stage_mark(ctx, PBF_STAGE_SORT, 1);
+  k = launch_sort(ctx->pred_o.p, c, g, n, &out, s);
+  stage_mark(ctx, PBF_STAGE_SORT, 0);
+  t.launches[PBF_STAGE_SORT] += k; launches += k;
+  ctx->sorted_buf = out;
+
+  stage_mark(ctx, PBF_STAGE_CELLS, 1);
+  k = launch_cells_reorder(g.keys[out], g.vals[out], ctx->pred_o.p, ctx->pos_o.p, ctx->pred_a.p, ctx->pos_s.p, g, n, s);
+  stage_mark(ctx, PBF_STAGE_CELLS, 0);
+  t.launches[PBF_STAGE_CELLS] += k; launches += k;
+
+  stage_mark(ctx, PBF_STAGE_NEIGHBORS, 1);
+  k = launch_neighbors(ctx->pred_a.p, c, g, nl, n, s);
+  stage_mark(ctx, PBF_STAGE_NEIGHBORS, 0);
+  t.launches[PBF_STAGE_NEIGHBORS] += k; launches += k;
+
+  SolveBuffers b{};
+  b.pred[0] = ctx->pred_a.p;
+  b.pred[1] = ctx->pred_b.p;
+  b.pos_s = ctx->pos_s.p;
+  b.vel[0] = ctx->vel_a.p;
+  b.vel[1] = ctx->vel_b.p;
+  b.omega = ctx->omega.p;
+  b.rho = ctx->rho.p;
+  b.planes = ctx->planes_dev.p;
+  b.pos_o = ctx->pos_o.p;
+  b.vel_o = ctx->vel_o.p;
+  b.status = ctx->status.p;
+  if (ctx->debug) {
+    b.dbg.lambda = ctx->dbg_lambda.p;
+    b.dbg.rho = ctx->dbg_rho.p;
+    b.dbg.delta = ctx->dbg_delta.p;
+    b.dbg.dv = ctx->dbg_dv.p;
+    b.dbg.eta = ctx->dbg_eta.p;
+  }
+  const int iters = ctx->params.solver_iterations;
+  k = launch_solve(b, nl, c, iters, n, ctx->mode == PBF_MODE_STRICT, s, stage_mark, ctx);
+  // attribute solver launches to their stages
+  if (iters > 0) {
+    t.launches[PBF_STAGE_LAMBDA] += iters;
+    t.launches[PBF_STAGE_DELTA] += iters;
+    if (c.do_xsph) t.launches[PBF_STAGE_XSPH] += 1;
+    if (c.do_vort) { t.launches[PBF_STAGE_VORT_OMEGA] += 1; t.launches[PBF_STAGE_VORT_APPLY] += 1; }
+  } else {
+    t.launches[PBF_STAGE_FINALIZE] += 1;
+  }
+  launches += k;
+  return launches;
+}
+
+int run_substeps(pbf_ctx* ctx, int nsteps) {
+  const bool graph = ctx->use_graph && !ctx->profile;
+  for (int sidx = 0; sidx < nsteps; ++sidx) {
+    if (graph) {
+      if (!ctx->graph_exec) {
+        cudaGraph_t gr = nullptr;
+        PBF_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        uint64_t saved[PBF_STAGE_COUNT];
+        std::memcpy(saved, ctx->timer.launches, sizeof(saved));
+        ctx->graph_kernels = enqueue_substep(ctx);
+        std::memcpy(ctx->timer.launches, saved, sizeof(saved));
+        PBF_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &gr));
+        PBF_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, gr, 0));
+        cudaGraphDestroy(gr);
+      }
+      PBF_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+      ctx->launch_count += (uint64_t)ctx->graph_kernels;
+    } else {
+      ctx->launch_count += (uint64_t)enqueue_substep(ctx);
+    }
+  }
+  PBF_CUDA(ctx, cudaGetLastError());
+  return PBF_OK;
+}
+
+int reset_status(pbf_ctx* ctx) {
+  StatusBlock z{};
+  for (int a = 0; a < 3; ++a) { z.min_cell[a] = INT_MAX; z.max_cell[a] = INT_MIN; }
+  *ctx->status_host = z;
+  PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status.p, ctx->status_host, sizeof(StatusBlock), cudaMemcpyHostToDevice, ctx->stream));
+  return PBF_OK;
+}
+
+template <typename T>
+int fetch(pbf_ctx* ctx, std::vector<T>& host, const T* dev, size_t count) {
+  host.resize(count);
+  if (count) PBF_CUDA(ctx, cudaMemcpy(host.data(), dev, count * sizeof(T), cudaMemcpyDeviceToHost));
+  return PBF_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+void pbf_default_params(pbf_params* p) {  // fluid::Params defaults, core.h:12-43
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->dt = 1.0f / 60.0f;
+  p->density = 6000.0f;
+  p->particle_mass = 0.0f;
+  p->h = 0.0f;
+  p->particle_radius = 0.01f;
+  p->epsilon = 600.0f;
+  p->solver_iterations = 4;
+  p->neighbor_reserve_factor = 1.5f;
+  p->use_uniform_grid = 1;
+  p->scorr_k = 0.00005f;
+  p->scorr_n = 4;
+  p->scorr_dq_coeff = 0.3f;
+  p->visc_c = 0.0002f;
+  p->vort_epsilon = 0.5f;
+  p->vort_norm_eps = 1e-6f;
+  p->external_force[1] = -9.8f;
+}
+
+int pbf_abi_version(void) { return PBF_ABI_VERSION; }
+
+int pbf_device_count(const char** err) {  // cuda_stub.cu:740-762
+  if (err) *err = nullptr;
+  int count = 0;
+  const cudaError_t e = cudaGetDeviceCount(&count);
+  if (e == cudaErrorNoDevice) return 0;
+  if (e != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(e);
+    g_error = cudaGetErrorString(e);
+    return PBF_E_CUDA;
+  }
+  return count;
+}
+
+pbf_ctx* pbf_create(int device, size_t capacity) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+              " (this backend has no CPU fallback)";
+    return nullptr;
+  }
+  if (device < 0 || device >= count) {
+    g_error = "device index out of range";
+    return nullptr;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  pbf_ctx* ctx = new pbf_ctx();
+  ctx->device = device;
+  pbf_default_params(&ctx->params);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMallocHost(reinterpret_cast<void**>(&ctx->status_host), sizeof(StatusBlock))) != cudaSuccess ||
+      (e = ctx->desc.reserve(1)) != cudaSuccess || (e = ctx->status.reserve(1)) != cudaSuccess ||
+      (e = ctx->planes_dev.reserve(kMaxPlanes)) != cudaSuccess) {
+    g_error = std::string("pbf_create: ") + cudaGetErrorString(e);
+    pbf_destroy(ctx);
+    return nullptr;
+  }
+  ctx->stream = ctx->own_stream;
+  if (capacity > 0 && ensure_particles(ctx, capacity) != PBF_OK) {
+    g_error = ctx->error;
+    pbf_destroy(ctx);
+    return nullptr;
+  }
+  return ctx;
+}
+
+void pbf_destroy(pbf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  invalidate_graph(ctx);
+  ctx->pos_o.release(); ctx->vel_o.release(); ctx->pos_bak.release(); ctx->vel_bak.release();
+  ctx->pred_o.release(); ctx->pred_a.release(); ctx->pred_b.release(); ctx->pos_s.release();
+  ctx->vel_a.release(); ctx->vel_b.release(); ctx->omega.release(); ctx->rho.release();
+  ctx->planes_dev.release(); ctx->desc.release(); ctx->status.release();
+  ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
+  ctx->hist.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
+  for (auto& b : ctx->soa) b.release();
+  ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
+  ctx->dbg_dv.release(); ctx->dbg_eta.release();
+  for (auto ev : ctx->timer.pool) cudaEventDestroy(ev);
+  for (auto ev : ctx->timer.begin) cudaEventDestroy(ev);
+  for (auto ev : ctx->timer.end) cudaEventDestroy(ev);
+  if (ctx->status_host) cudaFreeHost(ctx->status_host);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* pbf_last_error(const pbf_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int pbf_set_params(pbf_ctx* ctx, const pbf_params* p) {
+  if (!ctx || !p) return fail(ctx, PBF_E_INVALID, "pbf_set_params: null argument");
+  if (!(p->h > 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_set_params: h must be > 0 (the uniform-grid path needs a cell size)");
+  if (!p->use_uniform_grid)
+    return fail(ctx, PBF_E_INVALID, "pbf_set_params: use_uniform_grid=false (the O(N^2) path, core.cpp:248-268) is out of scope");
+  if (!(p->dt > 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_set_params: dt must be > 0");
+  if (p->solver_iterations < 0) return fail(ctx, PBF_E_INVALID, "pbf_set_params: solver_iterations < 0");
+  ctx->params = *p;
+  ctx->consts = make_consts(ctx->params, (int)ctx->planes_host.size());
+  invalidate_graph(ctx);
+  return PBF_OK;
+}
+
+int pbf_set_planes(pbf_ctx* ctx, int count, const float* nx, const float* ny, const float* nz, const float* d) {
+  if (!ctx || count < 0 || (count > 0 && (!nx || !ny || !nz || !d)))
+    return fail(ctx, PBF_E_INVALID, "pbf_set_planes: bad arguments");
+  if (count > kMaxPlanes) return fail(ctx, PBF_E_INVALID, "pbf_set_planes: more than 64 planes");
+  cudaSetDevice(ctx->device);
+  ctx->planes_host.resize(count);
+  for (int i = 0; i < count; ++i) ctx->planes_host[i] = make_float4(nx[i], ny[i], nz[i], d[i]);
+  if (count > 0) {
+    PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpy(ctx->planes_dev.p, ctx->planes_host.data(), count * sizeof(float4), cudaMemcpyHostToDevice));
+  }
+  ctx->consts = make_consts(ctx->params, count);
+  invalidate_graph(ctx);
+  return PBF_OK;
+}
+
+int pbf_set_mode(pbf_ctx* ctx, int mode) {
+  if (!ctx || (mode != PBF_MODE_STRICT && mode != PBF_MODE_FAST)) return fail(ctx, PBF_E_INVALID, "pbf_set_mode: bad mode");
+  if (mode != ctx->mode) invalidate_graph(ctx);
+  ctx->mode = mode;
+  return PBF_OK;
+}
+
+int pbf_set_stream(pbf_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return PBF_E_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  invalidate_graph(ctx);
+  return PBF_OK;
+}
+
+int pbf_set_graph(pbf_ctx* ctx, int enabled) {
+  if (!ctx) return PBF_E_INVALID;
+  ctx->use_graph = enabled != 0;
+  return PBF_OK;
+}
+
+int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py, const float* pz, const float* vx,
+               const float* vy, const float* vz) {
+  if (!ctx) return PBF_E_INVALID;
+  if (n > 0 && (!px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_upload: null array");
+  if (n > 0x7fffffffu - 64) return fail(ctx, PBF_E_INVALID, "pbf_upload: more than 2^31 particles in one slab");
+  cudaSetDevice(ctx->device);
+  int rc = ensure_particles(ctx, n);
+  if (rc != PBF_OK) return rc;
+  if (n != ctx->n) invalidate_graph(ctx);
+  ctx->n = n;
+  if (n == 0) return PBF_OK;
+  const float* src[6] = {px, py, pz, vx, vy, vz};
+  for (int a = 0; a < 6; ++a)
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->soa[a].p, src[a], n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  const float* dsoa[6] = {ctx->soa[0].p, ctx->soa[1].p, ctx->soa[2].p, ctx->soa[3].p, ctx->soa[4].p, ctx->soa[5].p};
+  ctx->launch_count += launch_pack_state(dsoa, ctx->pos_o.p, ctx->vel_o.p, (int)n, ctx->stream);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host arrays may be reused on return
+  return PBF_OK;
+}
+
+int pbf_download(pbf_ctx* ctx, float* px, float* py, float* pz, float* vx, float* vy, float* vz) {
+  if (!ctx) return PBF_E_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->n;
+  if (n == 0) return PBF_OK;
+  float* dst[6] = {px, py, pz, vx, vy, vz};
+  float* dsoa[6];
+  for (int a = 0; a < 6; ++a) dsoa[a] = dst[a] ? ctx->soa[a].p : nullptr;
+  ctx->launch_count += launch_unpack_state(ctx->pos_o.p, ctx->vel_o.p, dsoa, (int)n, ctx->stream);
+  for (int a = 0; a < 6; ++a)
+    if (dst[a]) PBF_CUDA(ctx, cudaMemcpyAsync(dst[a], ctx->soa[a].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PBF_OK;
+}
+
+int pbf_step(pbf_ctx* ctx, int nsteps) {
+  if (!ctx || nsteps < 0) return fail(ctx, PBF_E_INVALID, "pbf_step: bad arguments");
+  if (!(ctx->params.h > 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_step: parameters not set (h == 0)");
+  cudaSetDevice(ctx->device);
+  if (nsteps == 0) return PBF_OK;
+  if (ctx->n == 0) {  // core.cpp:122-125: only time advances
+    for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
+    return PBF_OK;
+  }
+  const size_t n = ctx->n;
+  // batch backup: a substep that overflows a device table is re-run after growing it
+  PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_bak.p, ctx->pos_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int attempt = 0; attempt < 12; ++attempt) {
+    int rc = ensure_tables(ctx);
+    if (rc != PBF_OK) return rc;
+    if ((rc = reset_status(ctx)) != PBF_OK) return rc;
+    if ((rc = run_substeps(ctx, nsteps)) != PBF_OK) return rc;
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status_host, ctx->status.p, sizeof(StatusBlock), cudaMemcpyDeviceToHost, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(&ctx->last_desc, ctx->desc.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, ctx->stream));
+    PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->profile) timer_resolve(ctx);
+    const StatusBlock st = *ctx->status_host;
+    ctx->last_status = st;
+    if (!st.grid_overflow && !st.nbr_overflow) {
+      for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;  // core.cpp:614
+      return PBF_OK;
+    }
+    // grow and replay the batch from the backup: results never depend on table sizes
+    ctx->batches_retried++;
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (st.grid_overflow) {
+      if (st.max_cells > (1ull << 30)) {
+        char buf[256];
+        std::snprintf(buf, sizeof(buf),
+                      "pbf_step: bounding grid needs %llu cells (> 2^30 dense-table limit); particle positions "
+                      "have diverged or are non-finite (state restored to the start of the batch)",
+                      (unsigned long long)st.max_cells);
+        return fail(ctx, PBF_E_CAPACITY, buf);
+      }
+      uint32_t cap = ctx->cell_cap;
+      while ((unsigned long long)cap < st.max_cells + st.max_cells / 4) cap <<= 1;
+      ctx->cell_cap = cap;
+      invalidate_graph(ctx);
+    }
+    if (st.nbr_overflow) {
+      const unsigned need = st.max_neighbors + st.max_neighbors / 4 + 8;
+      ctx->K = (int)((need + 7u) & ~7u);
+      invalidate_graph(ctx);
+    }
+  }
+  return fail(ctx, PBF_E_CAPACITY, "pbf_step: device tables kept overflowing after 12 growth attempts");
+}
+
+int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz, int nsteps) {
+  int rc = pbf_upload(ctx, n, px, py, pz, vx, vy, vz);
+  if (rc != PBF_OK) return rc;
+  if ((rc = pbf_step(ctx, nsteps)) != PBF_OK) return rc;
+  return pbf_download(ctx, px, py, pz, vx, vy, vz);
+}
+
+size_t pbf_count(const pbf_ctx* ctx) { return ctx ? ctx->n : 0; }
+float pbf_time(const pbf_ctx* ctx) { return ctx ? ctx->time : 0.0f; }
+int pbf_set_time(pbf_ctx* ctx, float t) {
+  if (!ctx) return PBF_E_INVALID;
+  ctx->time = t;
+  return PBF_OK;
+}
+
+// ---------------------------------------------------------------- parity surface
+int pbf_debug_enable(pbf_ctx* ctx, int enabled) {
+  if (!ctx) return PBF_E_INVALID;
+  if ((enabled != 0) != ctx->debug) invalidate_graph(ctx);
+  ctx->debug = enabled != 0;
+  return PBF_OK;
+}
+
+int pbf_debug_sizes(pbf_ctx* ctx, size_t* ncells, size_t* nneighbors) {
+  if (!ctx) return PBF_E_INVALID;
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nneighbors) *nneighbors = (size_t)ctx->last_status.total_neighbors;
+  if (ncells) {
+    size_t occupied = 0;
+    if (ctx->n) {
+      std::vector<int2> table;
+      int rc = fetch(ctx, table, ctx->cell_range.p, (size_t)ctx->last_desc.ncells);
+      if (rc != PBF_OK) return rc;
+      for (const int2& r : table) occupied += (r.y > r.x) ? 1 : 0;
+    }
+    *ncells = occupied;
+  }
+  return PBF_OK;
+}
+
+int pbf_debug_grid(pbf_ctx* ctx, int32_t* ecx, int32_t* ecy, int32_t* ecz, int32_t* eparticle,
+                   int32_t* cell_xyz, int32_t* cell_start, int32_t* cell_end) {
+  if (!ctx) return PBF_E_INVALID;
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const size_t n = ctx->n;
+  if (n == 0) return PBF_OK;
+  const GridDesc d = ctx->last_desc;
+  std::vector<uint32_t> keys, vals;
+  std::vector<int2> table;
+  int rc;
+  if ((rc = fetch(ctx, keys, ctx->sorted_buf ? ctx->keys1.p : ctx->keys0.p, n)) != PBF_OK) return rc;
+  if ((rc = fetch(ctx, vals, ctx->sorted_buf ? ctx->vals1.p : ctx->vals0.p, n)) != PBF_OK) return rc;
+  if ((rc = fetch(ctx, table, ctx->cell_range.p, (size_t)d.ncells)) != PBF_OK) return rc;
+  const uint32_t dy = (uint32_t)d.dim[1], dz = (uint32_t)d.dim[2];
+  auto decode = [&](uint32_t key, int32_t& x, int32_t& y, int32_t& z) {
+    z = (int32_t)(key % dz) + d.lo[2];
+    y = (int32_t)((key / dz) % dy) + d.lo[1];
+    x = (int32_t)(key / (dz * dy)) + d.lo[0];
+  };
+  for (size_t i = 0; i < n; ++i) {
+    int32_t x, y, z;
+    decode(keys[i], x, y, z);
+    if (ecx) ecx[i] = x;
+    if (ecy) ecy[i] = y;
+    if (ecz) ecz[i] = z;
+    if (eparticle) eparticle[i] = (int32_t)vals[i];
+  }
+  size_t k = 0;
+  for (uint32_t c = 0; c < d.ncells; ++c) {
+    const int2 r = table[c];
+    if (r.y <= r.x) continue;
+    int32_t x, y, z;
+    decode(c, x, y, z);
+    if (cell_xyz) { cell_xyz[3 * k] = x; cell_xyz[3 * k + 1] = y; cell_xyz[3 * k + 2] = z; }
+    if (cell_start) cell_start[k] = r.x;
+    if (cell_end) cell_end[k] = r.y;
+    ++k;
+  }
+  return PBF_OK;
+}
+
+int pbf_debug_neighbors(pbf_ctx* ctx, int32_t* prefix_sum, int32_t* indices) {
+  if (!ctx) return PBF_E_INVALID;
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const size_t n = ctx->n;
+  if (n == 0) return PBF_OK;
+  std::vector<uint32_t> vals, counts, list;
+  int rc;
+  if ((rc = fetch(ctx, vals, ctx->sorted_buf ? ctx->vals1.p : ctx->vals0.p, n)) != PBF_OK) return rc;
+  if ((rc = fetch(ctx, counts, ctx->nbr_count.p, n)) != PBF_OK) return rc;
+  const size_t K = (size_t)ctx->K;
+  if ((rc = fetch(ctx, list, ctx->nbr_idx.p, ((n + 31) / 32) * K * 32)) != PBF_OK) return rc;
+  std::vector<uint32_t> slot_of(n);
+  for (size_t s = 0; s < n; ++s) slot_of[vals[s]] = (uint32_t)s;
+  size_t total = 0;
+  for (size_t o = 0; o < n; ++o) {  // original particle order, like core.cpp:205
+    const size_t s = slot_of[o];
+    const uint32_t* row = list.data() + (s >> 5) * K * 32 + (s & 31);
+    for (uint32_t k = 0; k < counts[s]; ++k) {
+      if (indices) indices[total] = (int32_t)vals[row[(size_t)k * 32]];
+      ++total;
+    }
+    if (prefix_sum) prefix_sum[o] = (int32_t)total;
+  }
+  return PBF_OK;
+}
+
+int pbf_debug_scratch(pbf_ctx* ctx, int id, float* out) {
+  if (!ctx || !out || id < 0 || id >= PBF_SCRATCH_COUNT) return fail(ctx, PBF_E_INVALID, "pbf_debug_scratch: bad arguments");
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const size_t n = ctx->n;
+  if (n == 0) return PBF_OK;
+  int rc;
+  if (id <= PBF_SCRATCH_PRED_Z) {  // scratch.pred_* ends the step equal to the committed positions
+    std::vector<float4> pos;
+    if ((rc = fetch(ctx, pos, ctx->pos_o.p, n)) != PBF_OK) return rc;
+    for (size_t i = 0; i < n; ++i) out[i] = (&pos[i].x)[id - PBF_SCRATCH_PRED_X];
+    return PBF_OK;
+  }
+  std::vector<uint32_t> vals;
+  if ((rc = fetch(ctx, vals, ctx->sorted_buf ? ctx->vals1.p : ctx->vals0.p, n)) != PBF_OK) return rc;
+  auto need_debug = [&]() { return fail(ctx, PBF_E_INVALID, "pbf_debug_scratch: call pbf_debug_enable(ctx, 1) before stepping"); };
+  if (id == PBF_SCRATCH_LAMBDA || id == PBF_SCRATCH_RHO) {
+    if (!ctx->debug) return need_debug();
+    std::vector<float> v;
+    if ((rc = fetch(ctx, v, id == PBF_SCRATCH_LAMBDA ? ctx->dbg_lambda.p : ctx->dbg_rho.p, n)) != PBF_OK) return rc;
+    for (size_t s = 0; s < n; ++s) out[vals[s]] = v[s];
+    return PBF_OK;
+  }
+  const float4* src = nullptr;
+  int comp = 0;
+  if (id >= PBF_SCRATCH_DELTA_X && id <= PBF_SCRATCH_DELTA_Z) { src = ctx->dbg_delta.p; comp = id - PBF_SCRATCH_DELTA_X; if (!ctx->debug) return need_debug(); }
+  else if (id >= PBF_SCRATCH_DV_X && id <= PBF_SCRATCH_DV_Z) { src = ctx->dbg_dv.p; comp = id - PBF_SCRATCH_DV_X; if (!ctx->debug) return need_debug(); }
+  else if (id >= PBF_SCRATCH_OMEGA_X && id <= PBF_SCRATCH_OMEGA_MAG) { src = ctx->omega.p; comp = id - PBF_SCRATCH_OMEGA_X; }
+  else if (id >= PBF_SCRATCH_ETA_X && id <= PBF_SCRATCH_ETA_Z) { src = ctx->dbg_eta.p; comp = id - PBF_SCRATCH_ETA_X; if (!ctx->debug) return need_debug(); }
+  std::vector<float4> v;
+  if ((rc = fetch(ctx, v, src, n)) != PBF_OK) return rc;
+  for (size_t s = 0; s < n; ++s) out[vals[s]] = (&v[s].x)[comp];
+  return PBF_OK;
+}
+
+// ---------------------------------------------------------------- measurement surface
+static const char* kStageNames[PBF_STAGE_COUNT] = {"predict", "sort", "cells", "neighbors", "lambda", "delta",
+                                                   "xsph", "vort_omega", "vort_apply", "finalize", "exchange"};
+
+const char* pbf_stage_name(int stage) { return (stage >= 0 && stage < PBF_STAGE_COUNT) ? kStageNames[stage] : "?"; }
+
+int pbf_profile_enable(pbf_ctx* ctx, int enabled) {
+  if (!ctx) return PBF_E_INVALID;
+  ctx->profile = enabled != 0;
+  return PBF_OK;
+}
+
+int pbf_profile_reset(pbf_ctx* ctx) {
+  if (!ctx) return PBF_E_INVALID;
+  for (int s = 0; s < PBF_STAGE_COUNT; ++s) { ctx->timer.total_ms[s] = 0; ctx->timer.launches[s] = 0; }
+  return PBF_OK;
+}
+
+int pbf_profile_get(pbf_ctx* ctx, int stage, double* total_ms, uint64_t* launches) {
+  if (!ctx || stage < 0 || stage >= PBF_STAGE_COUNT) return PBF_E_INVALID;
+  if (total_ms) *total_ms = ctx->timer.total_ms[stage];
+  if (launches) *launches = ctx->timer.launches[stage];
+  return PBF_OK;
+}
+
+uint64_t pbf_launch_count(const pbf_ctx* ctx) { return ctx ? ctx->launch_count : 0; }
+
+// ---------------------------------------------------------------- slab decomposition
+// Implemented in pbf_slab.cu.
+
+}  // extern "C"
