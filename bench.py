@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — particle-substeps/s of the PBF substep on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--scene fluid_million] [--flags none|stable|all] [--mode strict|fast]
+                  [--presteps P] [--iterations I]
+
+A "step" is one PBF substep (reference core/src/core.cpp:119-615) over the whole scene.
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches` and `stages` are described in DESIGN.md §6.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+FLAGSETS = {
+    "none": dict(scorr=0, xsph=0, vort=0, rest=0.0, fric=0.0),
+    "stable": dict(scorr=1, xsph=1, vort=0, rest=0.05, fric=0.1),
+    "all": dict(scorr=1, xsph=1, vort=1, rest=0.05, fric=0.1),
+}
+
+# Algorithmic bytes per particle per launch (SURVEY.md §8d / DESIGN.md §5): each per-particle
+# array a pass logically consumes or produces, counted once; neighbour gathers and the
+# neighbour list are NOT algorithmic.
+ALG_BYTES = {
+    "predict": 48 + 8, "sort": 52, "cells": 6 + 52, "neighbors": 16,
+    "lambda": 16, "delta": 28, "xsph": 44, "vort_omega": 40, "vort_apply": 52,
+}
+
+
+def b_alg(iterations: int, flags: dict) -> int:
+    """B_alg = 254 + 44*I + 44*[xsph] + 92*[vorticity]."""
+    return 254 + 44 * iterations + 44 * int(bool(flags["xsph"])) + 92 * int(bool(flags["vort"]))
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_scene(name: str, flags: dict, iterations: int):
+    from fluidsimulator_b200 import scenes
+    if name in scenes.SCENES:
+        sc = scenes.SCENES[name]
+    elif name == "block_16m":
+        sc = scenes.block_16m()
+    elif name.startswith("weak_"):
+        sc = scenes.weak_block(int(name.split("_")[1]))
+    elif name.startswith("small_"):
+        sc = scenes.small_block(int(name.split("_")[1]))
+    else:
+        raise SystemExit(f"unknown scene {name}")
+    params, planes, state = scenes.load_scene(sc)
+    params.dt = np.float32(1.0 / 120.0)
+    params.enable_scorr, params.enable_xsph, params.enable_vorticity = flags["scorr"], flags["xsph"], flags["vort"]
+    params.plane_restitution, params.plane_friction = flags["rest"], flags["fric"]
+    params.solver_iterations = iterations
+    return params, planes, state
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+        for bit, name in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._once()
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self) -> dict:
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+            if not self.samples:
+                try:
+                    self._once()
+                except Exception:
+                    pass
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def time_cpu_reference(params, planes, state, steps: int, warmup: int):
+    """Times the reference's own CPU implementation (oracle/_ref when present, else the C port)
+    with all host threads.  Returns (seconds per step list, kind, threads)."""
+    from oracle.oracle_api import Oracle, best_kind
+    orc = Oracle(best_kind())
+    threads = os.cpu_count() or 1
+    orc.set_threads(threads)
+    orc.set_params(params)
+    orc.set_planes(planes)
+    orc.set_state(state)
+    for _ in range(warmup):
+        orc.step(1)
+    per = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.step(1)
+        per.append(time.perf_counter() - t0)
+    return per, orc.kind, min(threads, orc.max_threads())
+
+
+def run_reference(args, flags):
+    """--impl reference: the reference CPU path on the host cores, same metric / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    params, planes, state = load_scene(args.scene, flags, args.iterations)
+    n = len(state[0])
+    # bounded sample: keep the whole arm within a few minutes (≈2-3 s per 1M-particle substep)
+    budget_steps = args.steps + args.warmup
+    est = 2.5e-6 * n * budget_steps
+    sample = f"{args.scene} from t0, full scene ({n} particles) per step"
+    if est > 240.0:
+        keep = max(20000, int(n * 240.0 / est))
+        order = np.argsort(state[1], kind="stable")[:keep]  # the bottom `keep` particles of the block
+        order.sort()
+        state = [a[order].copy() for a in state]
+        n = keep
+        sample = f"{args.scene} from t0, bottom {keep} particles of the block per step (bounded sample)"
+    per, kind, threads = time_cpu_reference(params, planes, state, args.steps, args.warmup)
+    total = float(sum(per))
+    value = n * args.steps / total
+    line = {
+        "impl": "reference", "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.scene, "particles": n, "solver_iterations": args.iterations,
+                   "flags": args.flags, "dt": "1/120", "backend": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, flags):
+    import torch
+    from fluidsimulator_b200.capi import PBF_MODE_FAST, PBF_MODE_STRICT, Solver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        from fluidsimulator_b200 import multigpu
+        return multigpu.bench(args, flags, rank, world, local)
+
+    params, planes, state = load_scene(args.scene, flags, args.iterations)
+    n = len(state[0])
+    mode = PBF_MODE_STRICT if args.mode == "strict" else PBF_MODE_FAST
+    stream = torch.cuda.Stream()
+    sol = Solver(local, n, mode)
+    sol.set_params(params)
+    sol.set_planes(planes)
+    sol.set_stream(stream.cuda_stream)
+    sol.upload(state)
+
+    with torch.cuda.stream(stream):
+        if args.presteps:
+            sol.step(args.presteps)
+        sol.step(args.warmup)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        launches0 = sol.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        ev0.record(stream)
+        sol.step(args.steps)          # K substeps, device resident, one graph replay per substep
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = ev0.elapsed_time(ev1)
+        launches = sol.launch_count() - launches0
+        nbr_total = sol.debug_sizes()[1]
+
+        # per-stage CUDA-event timing of the same K substeps' successors (profiling disables the graph)
+        sol.profile_enable(True)
+        sol.profile_reset()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record(stream)
+        sol.step(args.steps)
+        pe1.record(stream)
+        torch.cuda.synchronize()
+        prof = sol.profile()
+        ms_prof = pe0.elapsed_time(pe1)
+        sol.profile_enable(False)
+
+        # e2e: the reference-facing call (cuda_step contract): pinned host arrays in and out every step
+        host = [torch.from_numpy(a).pin_memory().numpy() for a in sol.download()]
+        e2e_steps = max(3, min(args.steps, 20))
+        sol.step_host(host, 1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sol.step_host(host, 1)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+
+    value = n * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    stages = {}
+    for name, rec in prof.items():
+        if rec["launches"] and rec["ms"] > 0:
+            per_launch_ms = rec["ms"] / rec["launches"] * (3 if name == "sort" else 1)
+            stages[name] = {"ms_per_step": rec["ms"] / args.steps, "launches_per_step": rec["launches"] / args.steps}
+    solver = {k: v for k, v in stages.items() if k in ("lambda", "delta")}
+    dom = max(solver, key=lambda k: solver[k]["ms_per_step"]) if solver else None
+    roofline = None
+    if dom:
+        per_launch_s = 1e-3 * prof[dom]["ms"] / prof[dom]["launches"]
+        achieved = ALG_BYTES[dom] * n / per_launch_s / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "ncu_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get(f"{args.scene}:{dom}")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_particle": ALG_BYTES[dom], "avg_launch_ms": per_launch_s * 1e3,
+                    "whole_step_frac": b_alg(args.iterations, flags) * value / 1e9 / peak}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        per, kind, threads = time_cpu_reference(params, planes, state, steps=2, warmup=1)
+        cpu_baseline = {"value": n * len(per) / float(sum(per)), "unit": "particle-substeps/s", "cores": threads,
+                        "kind": kind, "sample": f"{args.scene} from t0, 1 warm-up + {len(per)} timed substeps, all host threads"}
+
+    line = {
+        "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.scene, "particles": n, "solver_iterations": args.iterations, "flags": args.flags,
+                   "mode": args.mode, "dt": "1/120", "presteps": args.presteps,
+                   "l2": f"working set exceeds L2: neighbour list {4 * nbr_total / 1e6:.0f} MB + {n * 16 * 9 / 1e6:.0f} MB of "
+                         "per-particle arrays are re-streamed every substep (no explicit flush)",
+                   "avg_neighbors": nbr_total / n},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": n * e2e_steps / e2e_s, "unit": "particle-substeps/s", "h2d_bytes_per_step": 24 * n,
+                "d2h_bytes_per_step": 24 * n, "steps": e2e_steps, "call": "pbf_step_host (cuda_step contract)"},
+        "gpu_launches": launches, "clocks": clocks, "stages": stages, "ms_per_step_profiled": ms_prof / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default=None)
+    ap.add_argument("--flags", default="stable", choices=list(FLAGSETS))
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--presteps", type=int, default=0)
+    ap.add_argument("--iterations", type=int, default=4)
+    ap.add_argument("--weak", action="store_true", help="multi-GPU: 2M particles per GPU instead of one fixed scene")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.scene is None:
+        args.scene = "fluid_million"
+    flags = FLAGSETS[args.flags]
+    if args.impl == "reference":
+        run_reference(args, flags)
+    else:
+        run_ours(args, flags)
+
+
+if __name__ == "__main__":
+    main()

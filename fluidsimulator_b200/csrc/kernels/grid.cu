@@ -168,24 +168,63 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, con
   for (int b = threadIdx.x; b < kRadixBins; b += kThreads) hist[b * nblocks + blockIdx.x] = sh[b];
 }
 
-// Exclusive scan of hist[digit*nblocks + block] (one block; m = 256*nblocks is small).
-constexpr int kScanThreads = 1024;
+// Exclusive scan of hist[digit*nblocks + block], two levels: every block scans one chunk of
+// kScanChunk entries in place and publishes the chunk total; the consumer (k_radix_scatter)
+// adds the exclusive prefix of the chunk totals, which it recomputes in shared memory (there
+// are only m / kScanChunk of them).
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanThreads * kScanItems;  // 2048 entries per block
 __global__ void __launch_bounds__(kScanThreads)
-k_radix_scan(uint32_t* __restrict__ hist, const StatusBlock* st, int m) {
+k_radix_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ chunk_total, const StatusBlock* st, int m) {
   __shared__ uint32_t warp_sums[kScanThreads / 32];
+  if (batch_failed(st)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (i0 + k < m) ? hist[i0 + k] : 0u;
+    tsum += v[k];
+  }
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t warp_excl = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    const uint32_t ws = warp_sums[w];
+    if (w < warp) warp_excl += ws;
+    total += ws;
+  }
+  uint32_t excl = warp_excl + (incl - tsum);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (i0 + k < m) hist[i0 + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
+}
+
+// Exclusive scan of the chunk totals, in place (one block; there are m / kScanChunk of them).
+__global__ void __launch_bounds__(1024)
+k_radix_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nchunks) {
+  __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_sh;
   if (batch_failed(st)) return;
   if (threadIdx.x == 0) carry_sh = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // coalesced tiles of 4 elements per thread
-  for (int base = 0; base < m; base += kScanThreads * 4) {
-    const int i0 = base + threadIdx.x * 4;
-    uint32_t v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < m) ? hist[i0 + k] : 0u;
-    const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
-    uint32_t incl = tsum;
+  for (int base = 0; base < nchunks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < nchunks) ? chunk_total[i] : 0u;
+    uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -194,25 +233,20 @@ k_radix_scan(uint32_t* __restrict__ hist, const StatusBlock* st, int m) {
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      uint32_t w = warp_sums[lane];
+      const uint32_t w = warp_sums[lane];
       uint32_t wi = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
         if (lane >= o) wi += t;
       }
-      warp_sums[lane] = wi - w;  // exclusive over warps
+      warp_sums[lane] = wi - w;
     }
     __syncthreads();
-    const uint32_t carry = carry_sh;
-    uint32_t excl = carry + warp_sums[warp] + (incl - tsum);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i0 + k < m) hist[i0 + k] = excl;
-      excl += v[k];
-    }
+    const uint32_t excl = carry_sh + warp_sums[warp] + (incl - v);
+    if (i < nchunks) chunk_total[i] = excl;
     __syncthreads();
-    if (threadIdx.x == kScanThreads - 1) carry_sh = excl;  // total so far
+    if (threadIdx.x == 1023) carry_sh = excl + v;
     __syncthreads();
   }
 }
@@ -222,13 +256,20 @@ k_radix_scan(uint32_t* __restrict__ hist, const StatusBlock* st, int m) {
 __global__ void __launch_bounds__(kThreads)
 k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                const uint32_t* __restrict__ offsets, const StatusBlock* st, int n, int nblocks, int shift) {
+                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ chunk_total,
+                const StatusBlock* st, int n, int nblocks, int shift) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kRounds = kSortTile / kThreads;  // per warp: kRounds x 32 consecutive keys
   __shared__ uint32_t whist[kWarps][kRadixBins];
+  __shared__ uint32_t digit_base[kRadixBins];
   if (batch_failed(st)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b = threadIdx.x; b < kWarps * kRadixBins; b += kThreads) (&whist[0][0])[b] = 0;
+  // global base of (digit, this block) = in-chunk exclusive scan + sum of the earlier chunk totals
+  for (int d = threadIdx.x; d < kRadixBins; d += kThreads) {
+    const int e = d * nblocks + blockIdx.x;
+    digit_base[d] = offsets[e] + chunk_total[e / kScanChunk];  // chunk_total is already an exclusive prefix
+  }
   __syncthreads();
 
   const int warp_base = blockIdx.x * kSortTile + warp * (kRounds * 32);
@@ -252,7 +293,7 @@ k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
   __syncthreads();
   // per digit: global base of this block, then exclusive scan over the warps
   for (int d = threadIdx.x; d < kRadixBins; d += kThreads) {
-    uint32_t running = offsets[d * nblocks + blockIdx.x];
+    uint32_t running = digit_base[d];
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       const uint32_t cnt = whist[w][d];
@@ -305,8 +346,10 @@ k_cells_reorder(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
 // ---------------------------------------------------------------- a7 neighbour list
 // Thread per sorted particle; candidates in the reference order: dz, dy, dx with dx
 // innermost (core.cpp:211-213), ascending slot (== ascending particle id) inside a cell.
-// Entry k of particle i lives at idx[(i/32)*K*32 + k*32 + i%32]: the k-th load of a
-// warp in the solver passes is one coalesced 128-byte line.
+// Two candidates are tested per step with packed f32x2 arithmetic (FADD2 / FMUL2; the
+// sums of products use scalar adds, see pbf_device.cuh).  Entry k of particle i lives at
+// idx[(i/32)*K*32 + (k/2)*64 + (i%32)*2 + k%2]: a solver pass reads two entries per lane
+// with one 8-byte load, 256 contiguous bytes per warp.
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
             const GridDesc* __restrict__ desc, uint32_t* __restrict__ nbr_idx,
@@ -320,24 +363,35 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
     const int cx = cell_coord(pi.x, inv_h) - desc->lo[0];
     const int cy = cell_coord(pi.y, inv_h) - desc->lo[1];
     const int cz = cell_coord(pi.z, inv_h) - desc->lo[2];
-    uint32_t* out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31);
+    uint32_t* out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
+    const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
+    const f2 xi = bcast(pi.x), yi = bcast(pi.y), zi = bcast(pi.z);
     for (int dz = -1; dz <= 1; ++dz)
       for (int dy = -1; dy <= 1; ++dy) {
         const uint32_t row = ((uint32_t)(cx - 1) * (uint32_t)dimy + (uint32_t)(cy + dy)) * (uint32_t)dimz +
                              (uint32_t)(cz + dz);
-        const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
+        int2 range[3];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) range[dx] = cell_range[row + (uint32_t)dx * xstride];
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const int2 range = cell_range[row + (uint32_t)dx * xstride];
-          for (int j = range.x; j < range.y; ++j) {
-            if (j == i) continue;
-            const float4 pj = pred_s[j];
-            const float ddx = __fsub_rn(pi.x, pj.x);
-            const float ddy = __fsub_rn(pi.y, pj.y);
-            const float ddz = __fsub_rn(pi.z, pj.z);
-            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
-            if (r2 < h2) {  // core.cpp:238
-              if (cnt < (uint32_t)K) out[(size_t)cnt * 32u] = (uint32_t)j;
+          for (int j = range[dx].x; j < range[dx].y; j += 2) {
+            const bool v1 = (j + 1) < range[dx].y;
+            const int j1 = v1 ? j + 1 : j;
+            const float4 a0 = pred_s[j];
+            const float4 a1 = pred_s[j1];
+            const f2 ddx = __fadd2_rn(xi, make_float2(-a0.x, -a1.x));
+            const f2 ddy = __fadd2_rn(yi, make_float2(-a0.y, -a1.y));
+            const f2 ddz = __fadd2_rn(zi, make_float2(-a0.z, -a1.z));
+            const f2 sx = __fmul2_rn(ddx, ddx), sy = __fmul2_rn(ddy, ddy), sz = __fmul2_rn(ddz, ddz);
+            const float r2a = __fadd_rn(__fadd_rn(sx.x, sy.x), sz.x);
+            const float r2b = __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y);
+            if (j != i && r2a < h2) {  // core.cpp:231-240
+              if (cnt < (uint32_t)K) out[(size_t)(cnt >> 1) * 64u + (cnt & 1u)] = (uint32_t)j;
+              ++cnt;
+            }
+            if (v1 && j1 != i && r2b < h2) {
+              if (cnt < (uint32_t)K) out[(size_t)(cnt >> 1) * 64u + (cnt & 1u)] = (uint32_t)j1;
               ++cnt;
             }
           }
@@ -398,12 +452,14 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
       k_keys_hist<<<nblocks, kThreads, 0, s>>>(pred_o, g.keys[0], g.hist, c.inv_h, g.desc, g.status, n, nblocks);
     else
       k_radix_hist<<<nblocks, kThreads, 0, s>>>(g.keys[cur], g.hist, g.status, n, nblocks, shift);
-    k_radix_scan<<<1, kScanThreads, 0, s>>>(g.hist, g.status, m);
+    const int nchunks = (m + kScanChunk - 1) / kScanChunk;
+    k_radix_scan<<<nchunks, kScanThreads, 0, s>>>(g.hist, g.chunk_total, g.status, m);
+    k_radix_scan_chunks<<<1, 1024, 0, s>>>(g.chunk_total, g.status, nchunks);
     k_radix_scatter<<<nblocks, kThreads, 0, s>>>(g.keys[cur], pass == 0 ? nullptr : g.vals[cur],
-                                                g.keys[cur ^ 1], g.vals[cur ^ 1], g.hist, g.status, n,
-                                                nblocks, shift);
+                                                g.keys[cur ^ 1], g.vals[cur ^ 1], g.hist, g.chunk_total,
+                                                g.status, n, nblocks, shift);
     cur ^= 1;
-    launches += 3;
+    launches += 4;
   }
   *out = cur;
   return launches;

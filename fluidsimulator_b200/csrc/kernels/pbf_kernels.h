@@ -22,13 +22,14 @@ struct GridBuffers {
   uint32_t* keys[2];
   uint32_t* vals[2];
   uint32_t* hist;       // kRadixBins * sort_blocks(n)
+  uint32_t* chunk_total;  // one per 2048 hist entries
   int2* cell_range;     // cell_cap entries
   uint32_t cell_cap;
   int sort_passes;      // ceil(log2(cell_cap) / 8)
 };
 
 struct NeighborList {
-  uint32_t* idx;     // [(ceil(n/32)) * K * 32]
+  uint32_t* idx;     // [(ceil(n/32)) * K * 32], pair-interleaved (see pbf_device.cuh); K even
   uint32_t* count;   // [n]
   int K;
 };

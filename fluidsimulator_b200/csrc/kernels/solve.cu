@@ -10,16 +10,21 @@
 //
 // Every pass is one thread per sorted particle walking its neighbour list (built once per
 // substep by k_neighbors, so the neighbour SET is the reference's: fixed at grid-build time,
-// re-tested with r2 < h2 on current positions).  The k-th list entry of a warp is one
-// coalesced 128-byte line; each neighbour costs one 16-byte gather because everything a pass
-// needs from particle j is packed into a single float4:
+// re-tested with r2 < h2 on current positions).  Two neighbours are processed per step with
+// Blackwell's packed f32x2 instructions (FADD2/FMUL2/FFMA2): one 8-byte list load brings two
+// indices (a coalesced 256-byte line pair per warp), each neighbour costs one 16-byte gather
+// because everything a pass needs from particle j is packed into a single float4:
 //   lambda pass   (pred.xyz, -)          delta pass   (pred.xyz, lambda_j)
 //   XSPH          (pos.xyz, -) + (vel.xyz, m/rho_j)
 //   omega pass    (pos.xyz, -) + (vel.xyz, -)          eta pass   (pos.xyz, |omega_j|)
+// and the per-neighbour terms are then accumulated in list order with scalar adds, so the
+// summation order is the reference's.
 //
-// Templated on the arithmetic type F: sfloat = STRICT (bit-identical to the CPU reference,
-// see pbf_device.cuh) or float = FAST.  The code below is written once, in the reference's
-// expression order.
+// STRICT = true: every operation is a correctly rounded IEEE binary32 op in the reference's
+// expression order (bit-identical to the CPU path).  STRICT = false: FMA contraction and
+// x*rsqrt(x); tolerance-gated.
+#include <type_traits>
+
 #include "pbf_kernels.h"
 
 namespace pbf {
@@ -27,87 +32,128 @@ namespace pbf {
 namespace {
 
 constexpr int kBlock = 128;
-constexpr int kUnroll = 4;  // list entries fetched per batch (independent gathers in flight)
+constexpr int kPairUnroll = 2;  // neighbour PAIRS fetched per batch (4 independent gathers in flight)
 
+template <bool S> using FT = typename std::conditional<S, sfloat, float>::type;
 template <typename F> struct V3 { F x, y, z; };
 
 __device__ __forceinline__ bool batch_failed(const StatusBlock* st) {
   return (st->grid_overflow | st->nbr_overflow) != 0;
 }
 
-// poly6_kernel (core.cpp:35-46): 0 if r2 > h2 else coeff * (h2-r2)^3
-template <typename F>
-__device__ __forceinline__ F poly6(F r2, const StepConsts& c) {
-  if (r2 > F(c.h2)) return F(0.0f);
-  const F diff = F(c.h2) - r2;
-  const F diff3 = diff * diff * diff;
-  return F(c.poly6_coeff) * diff3;
+// ---- pair iteration -----------------------------------------------------------------
+// body(a0, a1, v0, v1): data of the two neighbours of this step and their validity.
+template <typename Body>
+__device__ __forceinline__ void for_each_pair(const uint32_t* __restrict__ nbr_idx, int K, int i, uint32_t cnt,
+                                              const float4* __restrict__ a4, Body body) {
+  const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
+  for (uint32_t k = 0; k < cnt; k += 2 * kPairUnroll) {
+    uint2 j[kPairUnroll];
+    float4 a0[kPairUnroll], a1[kPairUnroll];
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      const uint32_t kk = k + 2 * u;
+      j[u] = (kk < cnt) ? row[(size_t)(kk >> 1) * 32u] : make_uint2((uint32_t)i, (uint32_t)i);
+      if (kk + 1 >= cnt) j[u].y = (uint32_t)i;  // odd tail: the slot was never written
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      a0[u] = a4[j[u].x];
+      a1[u] = a4[j[u].y];
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      const uint32_t kk = k + 2 * u;
+      if (kk < cnt) body(a0[u], a1[u], true, kk + 1 < cnt);
+    }
+  }
 }
 
-// spiky_gradient_factor (core.cpp:48-57): 0 if r > h else coeff * (h-r)^2
-template <typename F>
-__device__ __forceinline__ F spiky(F r, const StepConsts& c) {
-  if (r > F(c.h)) return F(0.0f);
-  const F diff = F(c.h) - r;
-  return F(c.spiky_coeff) * diff * diff;
+template <typename Body>
+__device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_idx, int K, int i, uint32_t cnt,
+                                               const float4* __restrict__ a4, const float4* __restrict__ b4,
+                                               Body body) {
+  const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
+  for (uint32_t k = 0; k < cnt; k += 2 * kPairUnroll) {
+    uint2 j[kPairUnroll];
+    float4 a0[kPairUnroll], a1[kPairUnroll], b0[kPairUnroll], b1[kPairUnroll];
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      const uint32_t kk = k + 2 * u;
+      j[u] = (kk < cnt) ? row[(size_t)(kk >> 1) * 32u] : make_uint2((uint32_t)i, (uint32_t)i);
+      if (kk + 1 >= cnt) j[u].y = (uint32_t)i;
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      a0[u] = a4[j[u].x];
+      a1[u] = a4[j[u].y];
+      b0[u] = b4[j[u].x];
+      b1[u] = b4[j[u].y];
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      const uint32_t kk = k + 2 * u;
+      if (kk < cnt) body(a0[u], a1[u], b0[u], b1[u], true, kk + 1 < cnt);
+    }
+  }
+}
+
+// ---- 2-wide geometry of a neighbour pair ---------------------------------------------
+template <bool S>
+struct PairGeom {
+  f2 dx, dy, dz, r2;
+  bool in0, in1;  // valid && r2 < h2 (core.cpp:302)
+};
+
+template <bool S>
+__device__ __forceinline__ PairGeom<S> pair_geom(float xi, float yi, float zi, float4 a0, float4 a1, bool v0, bool v1,
+                                                 const StepConsts& c) {
+  using M = M2<S>;
+  PairGeom<S> g;
+  g.dx = M::sub(bcast(xi), make_float2(a0.x, a1.x));
+  g.dy = M::sub(bcast(yi), make_float2(a0.y, a1.y));
+  g.dz = M::sub(bcast(zi), make_float2(a0.z, a1.z));
+  g.r2 = M::addp(M::addp(M::mul(g.dx, g.dx), M::mul(g.dy, g.dy)), M::mul(g.dz, g.dz));  // core.cpp:299
+  g.in0 = v0 && (g.r2.x < c.h2);
+  g.in1 = v1 && (g.r2.y < c.h2);
+  return g;
+}
+
+// poly6_kernel (core.cpp:35-46) on two r2 values: 0 if r2 > h2 else coeff * ((diff*diff)*diff)
+template <bool S>
+__device__ __forceinline__ f2 poly6_2(f2 r2, const StepConsts& c) {
+  using M = M2<S>;
+  const f2 diff = M::sub(bcast(c.h2), r2);
+  f2 w = M::mul(bcast(c.poly6_coeff), M::mul(M::mul(diff, diff), diff));
+  if (r2.x > c.h2) w.x = 0.0f;
+  if (r2.y > c.h2) w.y = 0.0f;
+  return w;
+}
+
+// spiky_gradient_factor(sqrt(max(r2, min_r2))) (core.cpp:48-57, 303-304) on two r2 values
+template <bool S>
+__device__ __forceinline__ f2 spiky_2(f2 r2, const StepConsts& c) {
+  using M = M2<S>;
+  const f2 rc = make_float2(r2.x < c.min_r2 ? c.min_r2 : r2.x, r2.y < c.min_r2 ? c.min_r2 : r2.y);
+  const f2 r = M::sqrt(rc, c.sqrt_safe != 0);
+  const f2 diff = M::sub(bcast(c.h), r);
+  f2 gf = M::mul(M::mul(bcast(c.spiky_coeff), diff), diff);
+  if (r.x > c.h) gf.x = 0.0f;
+  if (r.y > c.h) gf.y = 0.0f;
+  return gf;
 }
 
 // pow_ratio_n (core.cpp:59-71)
-template <typename F>
-__device__ __forceinline__ F pow_ratio(F ratio, int n) {
-  if (n == 2) return ratio * ratio;
-  if (n == 3) return ratio * ratio * ratio;
+template <bool S>
+__device__ __forceinline__ f2 pow_ratio_2(f2 ratio, int n) {
+  using M = M2<S>;
+  if (n == 2) return M::mul(ratio, ratio);
+  if (n == 3) return M::mul(M::mul(ratio, ratio), ratio);
   if (n == 4) {
-    const F r2 = ratio * ratio;
-    return r2 * r2;
+    const f2 r2 = M::mul(ratio, ratio);
+    return M::mul(r2, r2);
   }
-  return F(powf(Arith<F>::val(ratio), (float)n));  // not bit-pinned: no shipped scene reaches it
-}
-
-// clamp + sqrt of core.cpp:303
-template <typename F>
-__device__ __forceinline__ F clamped_r(F r2, const StepConsts& c) {
-  return Arith<F>::sqrt(r2 < F(c.min_r2) ? F(c.min_r2) : r2);
-}
-
-// Walks the neighbour list of sorted particle i; body(j, data_j...) is called in list order.
-// Gathers for kUnroll entries are issued before any of them is consumed.
-template <typename Body>
-__device__ __forceinline__ void for_each_neighbor(const uint32_t* __restrict__ nbr_idx, int K, int i,
-                                                  uint32_t cnt, const float4* __restrict__ a4, Body body) {
-  const uint32_t* row = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31);
-  for (uint32_t k = 0; k < cnt; k += kUnroll) {
-    uint32_t j[kUnroll];
-    float4 a[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) j[u] = (k + u < cnt) ? row[(size_t)(k + u) * 32u] : (uint32_t)i;
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) a[u] = a4[j[u]];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (k + u < cnt) body(j[u], a[u]);
-  }
-}
-
-template <typename Body>
-__device__ __forceinline__ void for_each_neighbor2(const uint32_t* __restrict__ nbr_idx, int K, int i,
-                                                   uint32_t cnt, const float4* __restrict__ a4,
-                                                   const float4* __restrict__ b4, Body body) {
-  const uint32_t* row = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31);
-  for (uint32_t k = 0; k < cnt; k += kUnroll) {
-    uint32_t j[kUnroll];
-    float4 a[kUnroll], b[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) j[u] = (k + u < cnt) ? row[(size_t)(k + u) * 32u] : (uint32_t)i;
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      a[u] = a4[j[u]];
-      b[u] = b4[j[u]];
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (k + u < cnt) body(j[u], a[u], b[u]);
-  }
+  return make_float2(powf(ratio.x, (float)n), powf(ratio.y, (float)n));  // not bit-pinned: no shipped scene reaches it
 }
 
 // a14 + scatter: restitution/friction on the committed position (core.cpp:579-610), then the
@@ -139,77 +185,98 @@ __device__ __forceinline__ void finalize_particle(float4 pos, V3<F> v, uint32_t 
 }
 
 // ---------------------------------------------------------------- a8 lambda
-template <typename F>
+template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
          const StatusBlock* st, DebugPtrs dbg, int K, int n) {
+  using M = M2<S>;
+  using F = FT<S>;
   if (batch_failed(st)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pred[i];
-  const F xi(pi.x), yi(pi.y), zi(pi.z);
-  F rho(0.0f), gsx(0.0f), gsy(0.0f), gsz(0.0f), sum_grad2(0.0f);
-  const F grad_scale(c.grad_scale);
-  for_each_neighbor(nbr_idx, K, i, nbr_count[i], pred, [&](uint32_t, float4 pj) {
-    const F dx = xi - F(pj.x), dy = yi - F(pj.y), dz = zi - F(pj.z);
-    const F r2 = dx * dx + dy * dy + dz * dz;
-    rho += poly6(r2, c);
-    if (r2 < F(c.h2)) {
-      const F gf = spiky(clamped_r(r2, c), c);
-      const F gx = gf * dx, gy = gf * dy, gz = gf * dz;
-      gsx += gx;
-      gsy += gy;
-      gsz += gz;
-      const F jx = -grad_scale * gx, jy = -grad_scale * gy, jz = -grad_scale * gz;
-      sum_grad2 += jx * jx + jy * jy + jz * jz;
+  float rho = 0.0f, gsx = 0.0f, gsy = 0.0f, gsz = 0.0f, sum_grad2 = 0.0f;
+  const f2 neg_scale = bcast(-c.grad_scale);
+  for_each_pair(nbr_idx, K, i, nbr_count[i], pred, [&](float4 a0, float4 a1, bool v0, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+    const f2 w = poly6_2<S>(g.r2, c);                     // rho += poly6(r2) (core.cpp:300)
+    const f2 gf = spiky_2<S>(g.r2, c);
+    const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
+    const f2 jx = M::mul(neg_scale, gx), jy = M::mul(neg_scale, gy), jz = M::mul(neg_scale, gz);
+    const f2 t = M::addp(M::addp(M::mul(jx, jx), M::mul(jy, jy)), M::mul(jz, jz));  // core.cpp:314-315
+    rho = M::adds(rho, w.x);
+    if (g.in0) {
+      gsx = M::adds(gsx, gx.x);
+      gsy = M::adds(gsy, gy.x);
+      gsz = M::adds(gsz, gz.x);
+      sum_grad2 = M::adds(sum_grad2, t.x);
+    }
+    if (v1) rho = M::adds(rho, w.y);
+    if (g.in1) {
+      gsx = M::adds(gsx, gx.y);
+      gsy = M::adds(gsy, gy.y);
+      gsz = M::adds(gsz, gz.y);
+      sum_grad2 = M::adds(sum_grad2, t.y);
     }
   });
-  rho += F(c.poly6_zero);
-  rho *= F(c.mass);
-  const F C = rho * F(c.inv_density) - F(1.0f);
-  const F ix = grad_scale * gsx, iy = grad_scale * gsy, iz = grad_scale * gsz;
-  sum_grad2 += ix * ix + iy * iy + iz * iz;
-  const F lambda = -C / (sum_grad2 + F(c.epsilon));
+  // core.cpp:319-328
+  F rho_f(rho), sg(sum_grad2);
+  rho_f += F(c.poly6_zero);
+  rho_f *= F(c.mass);
+  const F C = rho_f * F(c.inv_density) - F(1.0f);
+  const F grad_scale(c.grad_scale);
+  const F ix = grad_scale * F(gsx), iy = grad_scale * F(gsy), iz = grad_scale * F(gsz);
+  sg += ix * ix + iy * iy + iz * iz;
+  const F lambda = -C / (sg + F(c.epsilon));
   // only .w is written; concurrent readers of pred[i] use .xyz only in this pass
   reinterpret_cast<float*>(pred + i)[3] = Arith<F>::val(lambda);
-  rho_out[i] = Arith<F>::val(rho);
+  rho_out[i] = Arith<F>::val(rho_f);
   if (dbg.lambda) dbg.lambda[i] = Arith<F>::val(lambda);
-  if (dbg.rho) dbg.rho[i] = Arith<F>::val(rho);
+  if (dbg.rho) dbg.rho[i] = Arith<F>::val(rho_f);
 }
 
 // ---------------------------------------------------------------- a9 + a10 (+ a11, a14)
-// LAST: also velocity update / commit; FINAL: additionally restitution + scatter.
-template <typename F, bool LAST>
+// LAST: also velocity update / commit; is_final: additionally restitution + scatter.
+template <bool S, bool LAST>
 __global__ void __launch_bounds__(kBlock)
 k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
         const float4* __restrict__ pos_s, const float* __restrict__ rho, float4* __restrict__ vel_out,
         const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
         StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final, int K, int n) {
+  using M = M2<S>;
+  using F = FT<S>;
   if (batch_failed(st)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pred_in[i];
-  const F xi(pi.x), yi(pi.y), zi(pi.z), li(pi.w);
-  F ax(0.0f), ay(0.0f), az(0.0f);
-  for_each_neighbor(nbr_idx, K, i, nbr_count[i], pred_in, [&](uint32_t, float4 pj) {
-    const F dx = xi - F(pj.x), dy = yi - F(pj.y), dz = zi - F(pj.z);
-    const F r2 = dx * dx + dy * dy + dz * dz;
-    if (r2 < F(c.h2)) {
-      const F gf = spiky(clamped_r(r2, c), c);
-      F s = li + F(pj.w);
-      if (c.scorr_on) {
-        const F W = poly6(r2, c);
-        const F ratio = W * F(c.scorr_inv_wdq);
-        const F corr = F(c.scorr_negk) * pow_ratio(ratio, c.scorr_n);
-        s += corr;
-      }
-      ax += s * gf * dx;
-      ay += s * gf * dy;
-      az += s * gf * dz;
+  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  for_each_pair(nbr_idx, K, i, nbr_count[i], pred_in, [&](float4 a0, float4 a1, bool v0, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+    const f2 gf = spiky_2<S>(g.r2, c);
+    f2 s = M::add(bcast(pi.w), make_float2(a0.w, a1.w));  // lambda_i + lambda_j (core.cpp:355)
+    if (c.scorr_on) {                                      // core.cpp:356-361
+      const f2 w = poly6_2<S>(g.r2, c);
+      const f2 ratio = M::mul(w, bcast(c.scorr_inv_wdq));
+      const f2 corr = M::mul(bcast(c.scorr_negk), pow_ratio_2<S>(ratio, c.scorr_n));
+      s = M::addp(s, corr);
+    }
+    const f2 sg = M::mul(s, gf);                           // (s * grad_factor) * d (core.cpp:362-364)
+    const f2 tx = M::mul(sg, g.dx), ty = M::mul(sg, g.dy), tz = M::mul(sg, g.dz);
+    if (g.in0) {
+      sx = M::adds(sx, tx.x);
+      sy = M::adds(sy, ty.x);
+      sz = M::adds(sz, tz.x);
+    }
+    if (g.in1) {
+      sx = M::adds(sx, tx.y);
+      sy = M::adds(sy, ty.y);
+      sz = M::adds(sz, tz.y);
     }
   });
+  const F xi(pi.x), yi(pi.y), zi(pi.z);
+  F ax(sx), ay(sy), az(sz);
   ax *= F(c.inv_density);
   ay *= F(c.inv_density);
   az *= F(c.inv_density);
@@ -252,36 +319,46 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
 }
 
 // ---------------------------------------------------------------- a12 XSPH
-template <typename F>
+template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4* __restrict__ vel_out,
        const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
        const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
        float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final,
        int K, int n) {
+  using M = M2<S>;
+  using F = FT<S>;
   if (batch_failed(st)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pos[i];
   const float4 vi = vel_in[i];
-  const F xi(pi.x), yi(pi.y), zi(pi.z), vx(vi.x), vy(vi.y), vz(vi.z);
-  F sx(0.0f), sy(0.0f), sz(0.0f);
-  for_each_neighbor2(nbr_idx, K, i, nbr_count[i], pos, vel_in, [&](uint32_t, float4 pj, float4 vj) {
-    const F dx = xi - F(pj.x), dy = yi - F(pj.y), dz = zi - F(pj.z);
-    const F r2 = dx * dx + dy * dy + dz * dz;
-    if (r2 < F(c.h2)) {
-      const F W = poly6(r2, c);
-      const F inv_rho_j(vj.w);
-      sx += (F(vj.x) - vx) * W * inv_rho_j;
-      sy += (F(vj.y) - vy) * W * inv_rho_j;
-      sz += (F(vj.z) - vz) * W * inv_rho_j;
+  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel_in,
+                 [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v0, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+    const f2 w = poly6_2<S>(g.r2, c);
+    const f2 inv_rho = make_float2(b0.w, b1.w);
+    // ((v_j - v_i) * W) * inv_rho_j (core.cpp:449-451)
+    const f2 tx = M::mul(M::mul(M::sub(make_float2(b0.x, b1.x), bcast(vi.x)), w), inv_rho);
+    const f2 ty = M::mul(M::mul(M::sub(make_float2(b0.y, b1.y), bcast(vi.y)), w), inv_rho);
+    const f2 tz = M::mul(M::mul(M::sub(make_float2(b0.z, b1.z), bcast(vi.z)), w), inv_rho);
+    if (g.in0) {
+      sx = M::adds(sx, tx.x);
+      sy = M::adds(sy, ty.x);
+      sz = M::adds(sz, tz.x);
+    }
+    if (g.in1) {
+      sx = M::adds(sx, tx.y);
+      sy = M::adds(sy, ty.y);
+      sz = M::adds(sz, tz.y);
     }
   });
-  if (dbg.dv) dbg.dv[i] = make_float4(Arith<F>::val(sx), Arith<F>::val(sy), Arith<F>::val(sz), 0.0f);
+  if (dbg.dv) dbg.dv[i] = make_float4(sx, sy, sz, 0.0f);
   V3<F> v;  // core.cpp:461-465
-  v.x = vx + F(c.visc_c) * sx;
-  v.y = vy + F(c.visc_c) * sy;
-  v.z = vz + F(c.visc_c) * sz;
+  v.x = F(vi.x) + F(c.visc_c) * F(sx);
+  v.y = F(vi.y) + F(c.visc_c) * F(sy);
+  v.z = F(vi.z) + F(c.visc_c) * F(sz);
   if (is_final) {
     finalize_particle<F>(pi, v, __float_as_uint(pos_s[i].w), c, planes, pos_o, vel_o);
   } else {
@@ -290,73 +367,90 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
 }
 
 // ---------------------------------------------------------------- a13 vorticity, pass 1
-template <typename F>
+template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* __restrict__ omega,
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count, StepConsts c,
              const StatusBlock* st, int K, int n) {
+  using M = M2<S>;
+  using F = FT<S>;
   if (batch_failed(st)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pos[i];
   const float4 vi = vel[i];
-  const F xi(pi.x), yi(pi.y), zi(pi.z), vx(vi.x), vy(vi.y), vz(vi.z);
-  F ox(0.0f), oy(0.0f), oz(0.0f);
-  for_each_neighbor2(nbr_idx, K, i, nbr_count[i], pos, vel, [&](uint32_t, float4 pj, float4 vj) {
-    const F dx = xi - F(pj.x), dy = yi - F(pj.y), dz = zi - F(pj.z);
-    const F r2 = dx * dx + dy * dy + dz * dz;
-    if (r2 < F(c.h2)) {
-      const F gf = spiky(clamped_r(r2, c), c);
-      const F gx = gf * dx, gy = gf * dy, gz = gf * dz;
-      const F ux = F(vj.x) - vx, uy = F(vj.y) - vy, uz = F(vj.z) - vz;
-      ox += uy * gz - uz * gy;
-      oy += uz * gx - ux * gz;
-      oz += ux * gy - uy * gx;
+  float ox = 0.0f, oy = 0.0f, oz = 0.0f;
+  for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel,
+                 [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v0, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+    const f2 gf = spiky_2<S>(g.r2, c);
+    const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
+    const f2 ux = M::sub(make_float2(b0.x, b1.x), bcast(vi.x));
+    const f2 uy = M::sub(make_float2(b0.y, b1.y), bcast(vi.y));
+    const f2 uz = M::sub(make_float2(b0.z, b1.z), bcast(vi.z));
+    const f2 tx = M::subp(M::mul(uy, gz), M::mul(uz, gy));  // core.cpp:499-501
+    const f2 ty = M::subp(M::mul(uz, gx), M::mul(ux, gz));
+    const f2 tz = M::subp(M::mul(ux, gy), M::mul(uy, gx));
+    if (g.in0) {
+      ox = M::adds(ox, tx.x);
+      oy = M::adds(oy, ty.x);
+      oz = M::adds(oz, tz.x);
+    }
+    if (g.in1) {
+      ox = M::adds(ox, tx.y);
+      oy = M::adds(oy, ty.y);
+      oz = M::adds(oz, tz.y);
     }
   });
-  const F mag = Arith<F>::sqrt(ox * ox + oy * oy + oz * oz);  // core.cpp:507
-  float m = Arith<F>::val(mag);
-  if (!Arith<F>::strict && !(m == m)) m = 0.0f;  // x*rsqrt(x) at x == 0
-  omega[i] = make_float4(Arith<F>::val(ox), Arith<F>::val(oy), Arith<F>::val(oz), m);
+  const F fx(ox), fy(oy), fz(oz);
+  float m = __fsqrt_rn(Arith<F>::val(fx * fx + fy * fy + fz * fz));  // core.cpp:507
+  omega[i] = make_float4(ox, oy, oz, m);
   // |omega_i| rides in pos[i].w for the eta pass; readers of pos[] use .xyz only here
   reinterpret_cast<float*>(pos + i)[3] = m;
 }
 
 // ---------------------------------------------------------------- a13 pass 2 + apply (+ a14)
-template <typename F>
+template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ omega,
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
              const float4* __restrict__ pos_s, const float4* __restrict__ planes,
              float4* __restrict__ pos_o, float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st,
              DebugPtrs dbg, int K, int n) {
+  using M = M2<S>;
+  using F = FT<S>;
   if (batch_failed(st)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pos[i];
-  const F xi(pi.x), yi(pi.y), zi(pi.z), omi(pi.w);
-  F ex(0.0f), ey(0.0f), ez(0.0f);
-  for_each_neighbor(nbr_idx, K, i, nbr_count[i], pos, [&](uint32_t, float4 pj) {
-    const F dx = xi - F(pj.x), dy = yi - F(pj.y), dz = zi - F(pj.z);
-    const F r2 = dx * dx + dy * dy + dz * dz;
-    if (r2 < F(c.h2)) {
-      const F gf = spiky(clamped_r(r2, c), c);
-      const F gx = gf * dx, gy = gf * dy, gz = gf * dz;
-      const F coeff = F(pj.w) - omi;
-      ex += coeff * gx;
-      ey += coeff * gy;
-      ez += coeff * gz;
+  float ex = 0.0f, ey = 0.0f, ez = 0.0f;
+  for_each_pair(nbr_idx, K, i, nbr_count[i], pos, [&](float4 a0, float4 a1, bool v0, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+    const f2 gf = spiky_2<S>(g.r2, c);
+    const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
+    const f2 coeff = M::sub(make_float2(a0.w, a1.w), bcast(pi.w));  // |omega_j| - |omega_i| (core.cpp:534)
+    const f2 tx = M::mul(coeff, gx), ty = M::mul(coeff, gy), tz = M::mul(coeff, gz);
+    if (g.in0) {
+      ex = M::adds(ex, tx.x);
+      ey = M::adds(ey, ty.x);
+      ez = M::adds(ez, tz.x);
+    }
+    if (g.in1) {
+      ex = M::adds(ex, tx.y);
+      ey = M::adds(ey, ty.y);
+      ez = M::adds(ez, tz.y);
     }
   });
-  if (dbg.eta) dbg.eta[i] = make_float4(Arith<F>::val(ex), Arith<F>::val(ey), Arith<F>::val(ez), 0.0f);
+  if (dbg.eta) dbg.eta[i] = make_float4(ex, ey, ez, 0.0f);
   // core.cpp:547-570
-  const F len = Arith<F>::sqrt(ex * ex + ey * ey + ez * ez);
+  const F fex(ex), fey(ey), fez(ez);
+  const F len(__fsqrt_rn(Arith<F>::val(fex * fex + fey * fey + fez * fez)));
   F nx(0.0f), ny(0.0f), nz(0.0f);
   if (len > F(c.vort_norm_eps)) {
     const F inv = F(1.0f) / len;
-    nx = ex * inv;
-    ny = ey * inv;
-    nz = ez * inv;
+    nx = fex * inv;
+    ny = fey * inv;
+    nz = fez * inv;
   }
   const float4 om = omega[i];
   const F ox(om.x), oy(om.y), oz(om.z);
@@ -371,7 +465,7 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   finalize_particle<F>(pi, v, __float_as_uint(pos_s[i].w), c, planes, pos_o, vel_o);
 }
 
-template <typename F>
+template <bool S>
 int solve_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int iterations, int n,
                cudaStream_t s, StageCallback cb, void* user) {
   const int blocks = (n + kBlock - 1) / kBlock;
@@ -380,20 +474,18 @@ int solve_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& 
   auto stage = [&](int id, int begin) { if (cb) cb(user, id, begin); };
   const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
   const int final_in_delta = (!tail_xsph && !tail_vort) ? 1 : 0;
-  // 0 iterations: the predicted positions are committed unchanged; run the LAST delta variant
-  // on an empty list so the velocity update / commit still happens (core.cpp:277 loop skipped).
   for (int it = 0; it < iterations; ++it) {
     const bool last = (it == iterations - 1);
     stage(4, 1);
-    k_lambda<F><<<blocks, kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+    k_lambda<S><<<blocks, kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
     stage(4, 0);
     stage(5, 1);
     if (last)
-      k_delta<F, true><<<blocks, kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
+      k_delta<S, true><<<blocks, kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
                                                  b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg,
                                                  final_in_delta, nl.K, n);
     else
-      k_delta<F, false><<<blocks, kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
+      k_delta<S, false><<<blocks, kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
                                                   b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, 0,
                                                   nl.K, n);
     stage(5, 0);
@@ -404,7 +496,7 @@ int solve_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& 
   int vcur = 0;
   if (tail_xsph) {
     stage(6, 1);
-    k_xsph<F><<<blocks, kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
+    k_xsph<S><<<blocks, kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
                                         b.vel_o, c, b.status, b.dbg, tail_vort ? 0 : 1, nl.K, n);
     stage(6, 0);
     vcur = 1;
@@ -412,10 +504,10 @@ int solve_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& 
   }
   if (tail_vort) {
     stage(7, 1);
-    k_vort_omega<F><<<blocks, kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
+    k_vort_omega<S><<<blocks, kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
     stage(7, 0);
     stage(8, 1);
-    k_vort_apply<F><<<blocks, kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
+    k_vort_apply<S><<<blocks, kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
                                               b.pos_o, b.vel_o, c, b.status, b.dbg, nl.K, n);
     stage(8, 0);
     launches += 2;
@@ -424,11 +516,12 @@ int solve_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& 
 }
 
 // solver_iterations == 0: core.cpp:277 never runs, pred is committed as predicted.
-template <typename F>
+template <bool S>
 __global__ void __launch_bounds__(kBlock)
-k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s, float4* __restrict__ vel_out,
+k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
               const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
-              StepConsts c, const StatusBlock* st, int is_final, int n) {
+              StepConsts c, const StatusBlock* st, int n) {
+  using F = FT<S>;
   if (batch_failed(st)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -438,10 +531,7 @@ k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
   v.x = Arith<F>::div_dt(F(np.x) - F(p0.x), c.dt, c.inv_dt);
   v.y = Arith<F>::div_dt(F(np.y) - F(p0.y), c.dt, c.inv_dt);
   v.z = Arith<F>::div_dt(F(np.z) - F(p0.z), c.dt, c.inv_dt);
-  if (is_final)
-    finalize_particle<F>(np, v, __float_as_uint(p0.w), c, planes, pos_o, vel_o);
-  else
-    vel_out[i] = make_float4(Arith<F>::val(v.x), Arith<F>::val(v.y), Arith<F>::val(v.z), 0.0f);
+  finalize_particle<F>(np, v, __float_as_uint(p0.w), c, planes, pos_o, vel_o);
 }
 
 }  // namespace
@@ -456,15 +546,13 @@ int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts
     c0.do_xsph = 0;
     c0.do_vort = 0;
     if (strict)
-      k_commit_only<sfloat><<<blocks, kBlock, 0, s>>>(b.pred[0], b.pos_s, b.vel[0], b.planes, b.pos_o, b.vel_o, c0,
-                                                      b.status, 1, n);
+      k_commit_only<true><<<blocks, kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
     else
-      k_commit_only<float><<<blocks, kBlock, 0, s>>>(b.pred[0], b.pos_s, b.vel[0], b.planes, b.pos_o, b.vel_o, c0,
-                                                     b.status, 1, n);
+      k_commit_only<false><<<blocks, kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
     return 1;
   }
-  return strict ? solve_impl<sfloat>(b, nl, c, iterations, n, s, cb, cb_user)
-                : solve_impl<float>(b, nl, c, iterations, n, s, cb, cb_user);
+  return strict ? solve_impl<true>(b, nl, c, iterations, n, s, cb, cb_user)
+                : solve_impl<false>(b, nl, c, iterations, n, s, cb, cb_user);
 }
 
 }  // namespace pbf

@@ -86,6 +86,7 @@ StepConsts make_consts(const pbf_params& p, int nplanes) {
   c.do_xsph = (p.enable_xsph && p.visc_c != 0.0f) ? 1 : 0;
   c.do_vort = (p.enable_vorticity && p.vort_epsilon != 0.0f) ? 1 : 0;
   c.do_rest = ((p.plane_restitution > 0.0f || p.plane_friction > 0.0f) && nplanes > 0) ? 1 : 0;
+  c.sqrt_safe = (c.min_r2 >= 1e-30f && c.h2 <= 1e30f) ? 1 : 0;
   return c;
 }
 
@@ -123,6 +124,7 @@ int ensure_particles(pbf_ctx* ctx, size_t n) {
   PBF_CUDA(ctx, ctx->vals0.reserve(cap));
   PBF_CUDA(ctx, ctx->vals1.reserve(cap));
   PBF_CUDA(ctx, ctx->hist.reserve((size_t)kRadixBins * sort_blocks((int)cap)));
+  PBF_CUDA(ctx, ctx->chunk_total.reserve((size_t)kRadixBins * sort_blocks((int)cap) / 2048 + 2));
   PBF_CUDA(ctx, ctx->nbr_count.reserve(cap));
   for (auto& b : ctx->soa) PBF_CUDA(ctx, b.reserve(cap));
   ctx->cap = cap;
@@ -205,6 +207,7 @@ int enqueue_substep(pbf_ctx* ctx) {
   g.vals[0] = ctx->vals0.p;
   g.vals[1] = ctx->vals1.p;
   g.hist = ctx->hist.p;
+  g.chunk_total = ctx->chunk_total.p;
   g.cell_range = ctx->cell_range.p;
   g.cell_cap = ctx->cell_cap;
   g.sort_passes = sort_passes_for(ctx->cell_cap);
@@ -396,7 +399,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->vel_a.release(); ctx->vel_b.release(); ctx->omega.release(); ctx->rho.release();
   ctx->planes_dev.release(); ctx->desc.release(); ctx->status.release();
   ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
-  ctx->hist.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
+  ctx->hist.release(); ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
   ctx->dbg_dv.release(); ctx->dbg_eta.release();
@@ -651,9 +654,9 @@ int pbf_debug_neighbors(pbf_ctx* ctx, int32_t* prefix_sum, int32_t* indices) {
   size_t total = 0;
   for (size_t o = 0; o < n; ++o) {  // original particle order, like core.cpp:205
     const size_t s = slot_of[o];
-    const uint32_t* row = list.data() + (s >> 5) * K * 32 + (s & 31);
+    const uint32_t* row = list.data() + (s >> 5) * K * 32 + (s & 31) * 2;
     for (uint32_t k = 0; k < counts[s]; ++k) {
-      if (indices) indices[total] = (int32_t)vals[row[(size_t)k * 32]];
+      if (indices) indices[total] = (int32_t)vals[row[(size_t)(k >> 1) * 64 + (k & 1)]];
       ++total;
     }
     if (prefix_sum) prefix_sum[o] = (int32_t)total;
