@@ -168,6 +168,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    if path is None and os.environ.get("PBF_B200_LIB"):
+        path = os.environ["PBF_B200_LIB"]
     p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise RuntimeError(

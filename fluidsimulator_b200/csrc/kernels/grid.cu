@@ -387,11 +387,11 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
             const float r2a = __fadd_rn(__fadd_rn(sx.x, sy.x), sz.x);
             const float r2b = __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y);
             if (j != i && r2a < h2) {  // core.cpp:231-240
-              if (cnt < (uint32_t)K) out[(size_t)(cnt >> 1) * 64u + (cnt & 1u)] = (uint32_t)j;
+              if (cnt < (uint32_t)K) __stcs(out + (size_t)(cnt >> 1) * 64u + (cnt & 1u), (uint32_t)j);
               ++cnt;
             }
             if (v1 && j1 != i && r2b < h2) {
-              if (cnt < (uint32_t)K) out[(size_t)(cnt >> 1) * 64u + (cnt & 1u)] = (uint32_t)j1;
+              if (cnt < (uint32_t)K) __stcs(out + (size_t)(cnt >> 1) * 64u + (cnt & 1u), (uint32_t)j1);
               ++cnt;
             }
           }

@@ -31,8 +31,14 @@ namespace pbf {
 
 namespace {
 
-constexpr int kBlock = 128;
-constexpr int kPairUnroll = 2;  // neighbour PAIRS fetched per batch (4 independent gathers in flight)
+#ifndef PBF_SOLVE_BLOCK
+#define PBF_SOLVE_BLOCK 128
+#endif
+#ifndef PBF_PAIR_UNROLL
+#define PBF_PAIR_UNROLL 2
+#endif
+constexpr int kBlock = PBF_SOLVE_BLOCK;
+constexpr int kPairUnroll = PBF_PAIR_UNROLL;  // neighbour PAIRS fetched per batch (4 independent gathers in flight)
 
 template <bool S> using FT = typename std::conditional<S, sfloat, float>::type;
 template <typename F> struct V3 { F x, y, z; };
@@ -42,47 +48,53 @@ __device__ __forceinline__ bool batch_failed(const StatusBlock* st) {
 }
 
 // ---- pair iteration -----------------------------------------------------------------
-// body(a0, a1, v0, v1): data of the two neighbours of this step and their validity.
+// Walks the list of sorted slot i.  Full pairs run without any validity logic; an odd count
+// ends with one half-valid pair.  body(a0, a1, v1): data of the two neighbours and validity of the second.
+// List loads are streaming (ld.global.cs): every entry is used once per pass and must not
+// evict the gathered particle arrays from L1/L2.
 template <typename Body>
-__device__ __forceinline__ void for_each_pair(const uint32_t* __restrict__ nbr_idx, int K, int i, uint32_t cnt,
-                                              const float4* __restrict__ a4, Body body) {
+__device__ __forceinline__ void for_each_pair(const uint32_t* __restrict__ nbr_idx, int K, int i,
+                                              uint32_t cnt, const float4* __restrict__ a4, Body body) {
   const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
-  for (uint32_t k = 0; k < cnt; k += 2 * kPairUnroll) {
+  const uint32_t npairs = cnt >> 1;
+  uint32_t p = 0;
+  for (; p + kPairUnroll <= npairs; p += kPairUnroll) {
     uint2 j[kPairUnroll];
     float4 a0[kPairUnroll], a1[kPairUnroll];
 #pragma unroll
-    for (int u = 0; u < kPairUnroll; ++u) {
-      const uint32_t kk = k + 2 * u;
-      j[u] = (kk < cnt) ? row[(size_t)(kk >> 1) * 32u] : make_uint2((uint32_t)i, (uint32_t)i);
-      if (kk + 1 >= cnt) j[u].y = (uint32_t)i;  // odd tail: the slot was never written
-    }
+    for (int u = 0; u < kPairUnroll; ++u) j[u] = __ldcs(row + (size_t)(p + u) * 32u);
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) {
       a0[u] = a4[j[u].x];
       a1[u] = a4[j[u].y];
     }
 #pragma unroll
-    for (int u = 0; u < kPairUnroll; ++u) {
-      const uint32_t kk = k + 2 * u;
-      if (kk < cnt) body(a0[u], a1[u], true, kk + 1 < cnt);
-    }
+    for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], true);
+  }
+  for (; p < npairs; ++p) {
+    const uint2 j = __ldcs(row + (size_t)p * 32u);
+    const float4 a0 = a4[j.x], a1 = a4[j.y];
+    body(a0, a1, true);
+  }
+  if (cnt & 1u) {
+    const uint32_t j = __ldcs(reinterpret_cast<const uint32_t*>(row + (size_t)npairs * 32u));
+    const float4 a0 = a4[j];
+    body(a0, a4[i], false);
   }
 }
 
 template <typename Body>
-__device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_idx, int K, int i, uint32_t cnt,
-                                               const float4* __restrict__ a4, const float4* __restrict__ b4,
-                                               Body body) {
+__device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_idx, int K, int i,
+                                               uint32_t cnt, const float4* __restrict__ a4,
+                                               const float4* __restrict__ b4, Body body) {
   const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
-  for (uint32_t k = 0; k < cnt; k += 2 * kPairUnroll) {
+  const uint32_t npairs = cnt >> 1;
+  uint32_t p = 0;
+  for (; p + kPairUnroll <= npairs; p += kPairUnroll) {
     uint2 j[kPairUnroll];
     float4 a0[kPairUnroll], a1[kPairUnroll], b0[kPairUnroll], b1[kPairUnroll];
 #pragma unroll
-    for (int u = 0; u < kPairUnroll; ++u) {
-      const uint32_t kk = k + 2 * u;
-      j[u] = (kk < cnt) ? row[(size_t)(kk >> 1) * 32u] : make_uint2((uint32_t)i, (uint32_t)i);
-      if (kk + 1 >= cnt) j[u].y = (uint32_t)i;
-    }
+    for (int u = 0; u < kPairUnroll; ++u) j[u] = __ldcs(row + (size_t)(p + u) * 32u);
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) {
       a0[u] = a4[j[u].x];
@@ -91,10 +103,15 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
       b1[u] = b4[j[u].y];
     }
 #pragma unroll
-    for (int u = 0; u < kPairUnroll; ++u) {
-      const uint32_t kk = k + 2 * u;
-      if (kk < cnt) body(a0[u], a1[u], b0[u], b1[u], true, kk + 1 < cnt);
-    }
+    for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], b0[u], b1[u], true);
+  }
+  for (; p < npairs; ++p) {
+    const uint2 j = __ldcs(row + (size_t)p * 32u);
+    body(a4[j.x], a4[j.y], b4[j.x], b4[j.y], true);
+  }
+  if (cnt & 1u) {
+    const uint32_t j = __ldcs(reinterpret_cast<const uint32_t*>(row + (size_t)npairs * 32u));
+    body(a4[j], a4[i], b4[j], b4[i], false);
   }
 }
 
@@ -102,11 +119,11 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
 template <bool S>
 struct PairGeom {
   f2 dx, dy, dz, r2;
-  bool in0, in1;  // valid && r2 < h2 (core.cpp:302)
+  bool in0, in1;  // r2 < h2 (core.cpp:302), and the second neighbour exists
 };
 
 template <bool S>
-__device__ __forceinline__ PairGeom<S> pair_geom(float xi, float yi, float zi, float4 a0, float4 a1, bool v0, bool v1,
+__device__ __forceinline__ PairGeom<S> pair_geom(float xi, float yi, float zi, float4 a0, float4 a1, bool v1,
                                                  const StepConsts& c) {
   using M = M2<S>;
   PairGeom<S> g;
@@ -114,7 +131,7 @@ __device__ __forceinline__ PairGeom<S> pair_geom(float xi, float yi, float zi, f
   g.dy = M::sub(bcast(yi), make_float2(a0.y, a1.y));
   g.dz = M::sub(bcast(zi), make_float2(a0.z, a1.z));
   g.r2 = M::addp(M::addp(M::mul(g.dx, g.dx), M::mul(g.dy, g.dy)), M::mul(g.dz, g.dz));  // core.cpp:299
-  g.in0 = v0 && (g.r2.x < c.h2);
+  g.in0 = g.r2.x < c.h2;
   g.in1 = v1 && (g.r2.y < c.h2);
   return g;
 }
@@ -198,8 +215,8 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
   const float4 pi = pred[i];
   float rho = 0.0f, gsx = 0.0f, gsy = 0.0f, gsz = 0.0f, sum_grad2 = 0.0f;
   const f2 neg_scale = bcast(-c.grad_scale);
-  for_each_pair(nbr_idx, K, i, nbr_count[i], pred, [&](float4 a0, float4 a1, bool v0, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+  for_each_pair(nbr_idx, K, i, nbr_count[i], pred, [&](float4 a0, float4 a1, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
     const f2 w = poly6_2<S>(g.r2, c);                     // rho += poly6(r2) (core.cpp:300)
     const f2 gf = spiky_2<S>(g.r2, c);
     const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
@@ -252,8 +269,8 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
   if (i >= n) return;
   const float4 pi = pred_in[i];
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-  for_each_pair(nbr_idx, K, i, nbr_count[i], pred_in, [&](float4 a0, float4 a1, bool v0, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+  for_each_pair(nbr_idx, K, i, nbr_count[i], pred_in, [&](float4 a0, float4 a1, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
     const f2 gf = spiky_2<S>(g.r2, c);
     f2 s = M::add(bcast(pi.w), make_float2(a0.w, a1.w));  // lambda_i + lambda_j (core.cpp:355)
     if (c.scorr_on) {                                      // core.cpp:356-361
@@ -335,8 +352,8 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
   const float4 vi = vel_in[i];
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
   for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel_in,
-                 [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v0, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+                 [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
     const f2 w = poly6_2<S>(g.r2, c);
     const f2 inv_rho = make_float2(b0.w, b1.w);
     // ((v_j - v_i) * W) * inv_rho_j (core.cpp:449-451)
@@ -381,8 +398,8 @@ k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* _
   const float4 vi = vel[i];
   float ox = 0.0f, oy = 0.0f, oz = 0.0f;
   for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel,
-                 [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v0, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+                 [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
     const f2 gf = spiky_2<S>(g.r2, c);
     const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
     const f2 ux = M::sub(make_float2(b0.x, b1.x), bcast(vi.x));
@@ -424,8 +441,8 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   if (i >= n) return;
   const float4 pi = pos[i];
   float ex = 0.0f, ey = 0.0f, ez = 0.0f;
-  for_each_pair(nbr_idx, K, i, nbr_count[i], pos, [&](float4 a0, float4 a1, bool v0, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v0, v1, c);
+  for_each_pair(nbr_idx, K, i, nbr_count[i], pos, [&](float4 a0, float4 a1, bool v1) {
+    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
     const f2 gf = spiky_2<S>(g.r2, c);
     const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
     const f2 coeff = M::sub(make_float2(a0.w, a1.w), bcast(pi.w));  // |omega_j| - |omega_i| (core.cpp:534)

@@ -647,6 +647,7 @@ int pbf_debug_neighbors(pbf_ctx* ctx, int32_t* prefix_sum, int32_t* indices) {
   int rc;
   if ((rc = fetch(ctx, vals, ctx->sorted_buf ? ctx->vals1.p : ctx->vals0.p, n)) != PBF_OK) return rc;
   if ((rc = fetch(ctx, counts, ctx->nbr_count.p, n)) != PBF_OK) return rc;
+
   const size_t K = (size_t)ctx->K;
   if ((rc = fetch(ctx, list, ctx->nbr_idx.p, ((n + 31) / 32) * K * 32)) != PBF_OK) return rc;
   std::vector<uint32_t> slot_of(n);
@@ -725,6 +726,16 @@ int pbf_profile_get(pbf_ctx* ctx, int stage, double* total_ms, uint64_t* launche
 }
 
 uint64_t pbf_launch_count(const pbf_ctx* ctx) { return ctx ? ctx->launch_count : 0; }
+
+// Test hook (not in pbf_b200.h): shrink the device tables so the overflow -> grow -> replay
+// path of pbf_step can be exercised on small inputs.
+int pbf_debug_set_capacity(pbf_ctx* ctx, int K, uint32_t cell_cap) {
+  if (!ctx || K < 2 || cell_cap < 8) return PBF_E_INVALID;
+  ctx->K = (K + 1) & ~1;
+  ctx->cell_cap = cell_cap;
+  invalidate_graph(ctx);
+  return PBF_OK;
+}
 
 // ---------------------------------------------------------------- slab decomposition
 // Implemented in pbf_slab.cu.

@@ -104,3 +104,97 @@ def test_empty_state_advances_time(built):
     for _ in range(3):
         t = np.float32(t + np.float32(params.dt))
     assert np.float32(sol.time) == t
+
+
+# ---- against the committed golden fixtures (outputs of the unmodified reference) -----------
+import golden_util as G  # noqa: E402
+
+FLAGSETS = {"none": H.NO_FLAGS, "stable": H.STABLE_FLAGS, "all": H.ALL_FLAGS}
+
+
+def _solver(scene, flags, iterations=None, mode=PBF_MODE_STRICT):
+    from fluidsimulator_b200.capi import Solver
+    params, planes, state = scenes.load_scene(scene)
+    params = H.configure(params, flags, iterations=iterations)
+    sol = Solver(0, len(state[0]), mode)
+    sol.set_params(params)
+    sol.set_planes(planes)
+    sol.debug_enable(True)
+    sol.upload(state)
+    return sol
+
+
+@pytest.mark.parametrize("flagname", list(FLAGSETS))
+def test_strict_matches_golden_small(built, flagname):
+    flags = FLAGSETS[flagname]
+    gold = G.load_small(flagname)
+    sol = _solver(scenes.small_block(10), flags)
+    done = 0
+    for step in sorted(gold):
+        sol.step(step - done)
+        done = step
+        assert G.mismatches(G.snapshot_of(sol, flags, True), gold[step]) == [], f"step {step}"
+        assert np.float32(sol.time) == gold[step]["time"]
+
+
+@pytest.mark.parametrize("run", ["fluid_large:stable", "fluid_large:all", "fluid_large:all:iters8"])
+def test_strict_matches_golden_digests(built, run):
+    gold = G.digests()["runs"][run]
+    parts = run.split(":")
+    flags = FLAGSETS[parts[1]]
+    sol = _solver(scenes.SCENES[parts[0]], flags, 8 if len(parts) > 2 else None)
+    done = 0
+    for step in sorted(int(s) for s in gold):
+        sol.step(step - done)
+        done = step
+        assert G.digest_mismatches(G.snapshot_of(sol, flags, True), gold[str(step)]) == [], f"step {step}"
+
+
+def test_neighbor_capacity_growth_is_transparent(built):
+    """A batch that overflows the neighbour table is re-run after growing it; results are unchanged."""
+    import ctypes as C
+    flags = H.STABLE_FLAGS
+    gold = G.load_small("stable")
+    sol = _solver(scenes.small_block(10), flags)
+    sol.lib.pbf_debug_set_capacity.restype = C.c_int
+    sol.lib.pbf_debug_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    assert sol.lib.pbf_debug_set_capacity(sol.ctx, 8, 64) == 0   # K = 8 neighbours, 64 grid cells
+    sol.step(5)
+    assert G.mismatches(G.snapshot_of(sol, flags, True), gold[5]) == []
+
+
+def test_fluid_million_properties(built):
+    """Full-size scene (BASELINE.json size): size-independent properties instead of a CPU replay.
+    Sortedness and completeness of the grid tables, symmetry of the neighbour relation, and
+    equality of the STRICT result regardless of batching / graph replay."""
+    from fluidsimulator_b200.capi import Solver
+    params, planes, state = scenes.load_scene(scenes.SCENES["fluid_million"])
+    params = H.configure(params, H.STABLE_FLAGS)
+    n = len(state[0])
+    outs = []
+    for graph, chunks in ((True, [6]), (False, [1, 2, 3])):
+        sol = Solver(0, n)
+        sol.set_params(params)
+        sol.set_planes(planes)
+        sol.set_graph(graph)
+        sol.upload(state)
+        for c in chunks:
+            sol.step(c)
+        outs.append(sol.download())
+        if graph:
+            g = sol.debug_grid()
+            key = (g["entry_cx"].astype(np.int64) << 42) + (g["entry_cy"].astype(np.int64) << 21) + g["entry_cz"]
+            assert np.all(np.diff(key) >= 0)                                  # sorted by (x, y, z)
+            same = np.diff(key) == 0
+            assert np.all(np.diff(g["entry_particle"].astype(np.int64))[same] > 0)   # ties by ascending id
+            assert np.array_equal(np.sort(g["entry_particle"]), np.arange(n, dtype=np.int32))  # a permutation
+            assert g["cell_start"][0] == 0 and g["cell_end"][-1] == n
+            assert np.array_equal(g["cell_start"][1:], g["cell_end"][:-1])    # cells tile the sorted order
+            prefix, idx = sol.debug_neighbors()
+            counts = np.diff(np.concatenate([[0], prefix]))
+            owner = np.repeat(np.arange(n, dtype=np.int64), counts)
+            fwd = np.sort(owner * n + idx)
+            bwd = np.sort(idx.astype(np.int64) * n + owner)
+            assert np.array_equal(fwd, bwd)                                   # j in N(i) <=> i in N(j)
+    for a, b in zip(*outs):
+        assert H.bit_equal(a, b)
