@@ -1,0 +1,34 @@
+// cuda_backend.hpp — the three entry points the reference application binds for its CUDA
+// backend (reference cuda/include/fluid/cuda.h:7-9), re-created on top of the C ABI.
+#pragma once
+
+#ifdef PBF_USE_REFERENCE_HEADERS
+#include "fluid/core.h"   // the reference's own header (drop-in build)
+#else
+#include "fluid_types.hpp"
+#endif
+
+namespace fluid {
+
+int cuda_version();                                           // cuda.h:7
+bool cuda_device_available(int* count, const char** error);   // cuda.h:8
+void cuda_step(const Params& params, State& state);           // cuda.h:9
+
+// Extensions used by this repo's own application (device-resident stepping, row f1 of
+// SURVEY §8): the same backend object cuda_step uses, without the per-call host round trip.
+namespace b200 {
+struct Options {
+  int device = 0;
+  bool fast_mode = false;  // PBF_MODE_FAST instead of the bit-exact default
+};
+void configure(const Options& options);            // before the first step
+void upload(const Params& params, const State& state);
+void step_resident(const Params& params, int nsteps);   // no host traffic
+void download_positions(State& state);             // pos_* only (what the VTK writer reads)
+void download(State& state);                       // pos_* and vel_*
+float device_time();
+void set_device_time(float t);
+void shutdown();
+}  // namespace b200
+
+}  // namespace fluid

@@ -1,0 +1,185 @@
+// cuda_shim.cpp — fluid::cuda_version / cuda_device_available / cuda_step over the C ABI.
+//
+// Replaces reference cuda/src/cuda_stub.cu:736-1099 behind the call site
+// app/src/main.cpp:171-187 (probe) and :250-254 (step).  Contract kept:
+//   - caller owns Params/State; on return pos_*/vel_* hold the new values in original particle
+//     order and state.time is advanced by dt (float accumulate, core.cpp:614);
+//   - state.cpu is left untouched (the reference CUDA backend does the same);
+//   - empty state: only time advances (cuda_stub.cu:765-769).
+// Difference: CUDA failures are not silent.  The reference checks no error codes; here any
+// failure prints the reason to stderr and aborts — main() has no recovery path either way.
+#include "cuda_backend.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "pbf_b200.h"
+
+namespace fluid {
+namespace {
+
+struct Backend {
+  pbf_ctx* ctx = nullptr;
+  b200::Options options;
+  pbf_params last_params{};
+  bool params_valid = false;
+  std::vector<float> plane_cache;  // nx.., ny.., nz.., d.. of the planes last sent
+};
+
+Backend& backend() {
+  static Backend b;
+  return b;
+}
+
+[[noreturn]] void die(const char* what, pbf_ctx* ctx) {
+  std::fprintf(stderr, "pbf_b200 backend: %s failed: %s\n", what, pbf_last_error(ctx));
+  std::abort();
+}
+
+void check(int rc, const char* what) {
+  if (rc != PBF_OK) die(what, backend().ctx);
+}
+
+pbf_ctx* context(std::size_t capacity) {
+  Backend& b = backend();
+  if (!b.ctx) {
+    b.ctx = pbf_create(b.options.device, capacity);
+    if (!b.ctx) die("pbf_create", nullptr);
+    check(pbf_set_mode(b.ctx, b.options.fast_mode ? PBF_MODE_FAST : PBF_MODE_STRICT), "pbf_set_mode");
+  }
+  return b.ctx;
+}
+
+pbf_params to_pod(const Params& p) {
+  pbf_params q;
+  std::memset(&q, 0, sizeof(q));
+  q.dt = p.dt;
+  q.density = p.density;
+  q.particle_mass = p.particle_mass;
+  q.h = p.h;
+  q.particle_radius = p.particle_radius;
+  q.epsilon = p.epsilon;
+  q.solver_iterations = p.solver_iterations;
+  q.neighbor_reserve_factor = p.neighbor_reserve_factor;
+  q.use_uniform_grid = p.use_uniform_grid ? 1 : 0;
+  q.enable_scorr = p.enable_scorr ? 1 : 0;
+  q.enable_xsph = p.enable_xsph ? 1 : 0;
+  q.enable_vorticity = p.enable_vorticity ? 1 : 0;
+  q.scorr_k = p.scorr_k;
+  q.scorr_n = p.scorr_n;
+  q.scorr_dq_coeff = p.scorr_dq_coeff;
+  q.visc_c = p.visc_c;
+  q.plane_restitution = p.plane_restitution;
+  q.plane_friction = p.plane_friction;
+  q.vort_epsilon = p.vort_epsilon;
+  q.vort_norm_eps = p.vort_norm_eps;
+  q.external_force[0] = p.external_forces.x;
+  q.external_force[1] = p.external_forces.y;
+  q.external_force[2] = p.external_forces.z;
+  return q;
+}
+
+// Params are re-sent only when they changed (cuda_step receives them on every call).
+void sync_params(const Params& params, std::size_t capacity) {
+  Backend& b = backend();
+  pbf_ctx* ctx = context(capacity);
+  const std::size_t np = params.planes.size();
+  std::vector<float> planes;
+  planes.reserve(4 * np);
+  planes.insert(planes.end(), params.planes.nx.begin(), params.planes.nx.end());
+  planes.insert(planes.end(), params.planes.ny.begin(), params.planes.ny.end());
+  planes.insert(planes.end(), params.planes.nz.begin(), params.planes.nz.end());
+  planes.insert(planes.end(), params.planes.d.begin(), params.planes.d.end());
+  if (!b.params_valid || planes != b.plane_cache) {
+    check(pbf_set_planes(ctx, static_cast<int>(np), planes.data(), planes.data() + np, planes.data() + 2 * np,
+                         planes.data() + 3 * np),
+          "pbf_set_planes");
+    b.plane_cache = planes;
+    b.params_valid = false;
+  }
+  const pbf_params pod = to_pod(params);
+  if (!b.params_valid || std::memcmp(&pod, &b.last_params, sizeof(pod)) != 0) {
+    check(pbf_set_params(ctx, &pod), "pbf_set_params");
+    b.last_params = pod;
+    b.params_valid = true;
+  }
+}
+
+}  // namespace
+
+int cuda_version() { return 1; }  // cuda_stub.cu:736-738
+
+bool cuda_device_available(int* count, const char** error) {  // cuda_stub.cu:740-762
+  if (count) *count = 0;
+  if (error) *error = nullptr;
+  const char* err = nullptr;
+  const int n = pbf_device_count(&err);
+  if (n < 0) {
+    if (error) *error = err;
+    return false;
+  }
+  if (count) *count = n;
+  return n > 0;
+}
+
+void cuda_step(const Params& params, State& state) {  // cuda_stub.cu:764-1099
+  const std::size_t n = state.size();
+  if (n == 0) {
+    state.time += params.dt;
+    return;
+  }
+  sync_params(params, n);
+  pbf_ctx* ctx = backend().ctx;
+  check(pbf_set_time(ctx, state.time), "pbf_set_time");
+  check(pbf_step_host(ctx, n, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), state.vel_x.data(),
+                      state.vel_y.data(), state.vel_z.data(), 1),
+        "pbf_step_host");
+  state.time = pbf_time(ctx);
+}
+
+namespace b200 {
+
+void configure(const Options& options) { backend().options = options; }
+
+void upload(const Params& params, const State& state) {
+  sync_params(params, state.size());
+  pbf_ctx* ctx = backend().ctx;
+  check(pbf_upload(ctx, state.size(), state.pos_x.data(), state.pos_y.data(), state.pos_z.data(),
+                   state.vel_x.data(), state.vel_y.data(), state.vel_z.data()),
+        "pbf_upload");
+  check(pbf_set_time(ctx, state.time), "pbf_set_time");
+}
+
+void step_resident(const Params& params, int nsteps) {
+  sync_params(params, pbf_count(backend().ctx));
+  check(pbf_step(backend().ctx, nsteps), "pbf_step");
+}
+
+void download_positions(State& state) {
+  pbf_ctx* ctx = backend().ctx;
+  check(pbf_download(ctx, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), nullptr, nullptr, nullptr),
+        "pbf_download");
+  state.time = pbf_time(ctx);
+}
+
+void download(State& state) {
+  pbf_ctx* ctx = backend().ctx;
+  check(pbf_download(ctx, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), state.vel_x.data(),
+                     state.vel_y.data(), state.vel_z.data()),
+        "pbf_download");
+  state.time = pbf_time(ctx);
+}
+
+float device_time() { return pbf_time(backend().ctx); }
+void set_device_time(float t) { check(pbf_set_time(backend().ctx, t), "pbf_set_time"); }
+
+void shutdown() {
+  Backend& b = backend();
+  if (b.ctx) pbf_destroy(b.ctx);
+  b.ctx = nullptr;
+  b.params_valid = false;
+}
+
+}  // namespace b200
+}  // namespace fluid

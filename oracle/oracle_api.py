@@ -22,6 +22,8 @@ from fluidsimulator_b200.capi import PbfParams, SCRATCH_IDS, fptr, iptr  # noqa:
 REF_SO = _HERE / "_ref" / "libpbf_oracle_ref.so"
 PORT_SO = _HERE / "_build" / "libpbf_oracle_port.so"
 REFERENCE_ROOT = Path("/root/reference")
+DROPIN_BIN = _HERE / "_ref" / "fluidsim_dropin"   # reference main + this repo's backend
+REFAPP_BIN = _HERE / "_ref" / "fluidsim_ref"      # reference incl. its own CUDA backend (sm_100)
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -33,7 +35,7 @@ def build(which: str = "all", quiet: bool = True) -> None:
     if which in ("all", "port"):
         targets.append("port")
     if which in ("all", "ref") and (REFERENCE_ROOT / "core/src/core.cpp").exists():
-        targets.append("ref")
+        targets += ["ref", "dropin", "refapp"]
     for t in targets:
         subprocess.run(["make", "-C", str(_HERE), t], check=True,
                        stdout=subprocess.DEVNULL if quiet else None)
