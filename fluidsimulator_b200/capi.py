@@ -157,6 +157,16 @@ ABI = {
     "pbf_slab_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
     "pbf_slab_owned": (C.c_size_t, [C.c_void_p]),
     "pbf_slab_download": (C.c_int, [C.c_void_p, _i64p] + [_f32p] * 6),
+    "pbf_slab_upload_owned": (C.c_int, [C.c_void_p, C.c_size_t, _i64p] + [_f32p] * 6),
+    "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
+    "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
+    "pbf_slab_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32p, _i32p]),
+    "pbf_group_create": (C.c_void_p, [C.POINTER(C.c_void_p), C.c_int]),
+    "pbf_group_destroy": (None, [C.c_void_p]),
+    "pbf_group_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
+    "pbf_group_step": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_group_download": (C.c_int, [C.c_void_p] + [_f32p] * 6),
+    "pbf_group_count": (C.c_size_t, [C.c_void_p]),
 }
 
 _lib = None
@@ -325,3 +335,115 @@ def device_count() -> int:
     lib = load_library()
     err = C.c_char_p()
     return int(lib.pbf_device_count(C.byref(err)))
+
+
+def slab_plan(px: np.ndarray, h: float, nranks: int) -> np.ndarray:
+    """pbf_slab_plan: x-cell cuts [nranks + 1] for `nranks` slabs (host only, no GPU needed)."""
+    lib = load_library()
+    px = np.ascontiguousarray(px, dtype=np.float32)
+    cuts = np.empty(nranks + 1, dtype=np.int32)
+    rc = lib.pbf_slab_plan(px.shape[0], fptr(px), C.c_float(h), nranks, iptr(cuts))
+    if rc != 0:
+        raise PbfError(f"pbf_slab_plan failed ({rc}): {(lib.pbf_last_error(None) or b'?').decode()}")
+    return cuts
+
+
+def comm_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(PBF_COMM_ID_BYTES)
+    rc = lib.pbf_comm_unique_id(buf)
+    if rc != 0:
+        raise PbfError(f"pbf_comm_unique_id failed ({rc}): {(lib.pbf_last_error(None) or b'?').decode()}")
+    return buf.raw
+
+
+class SlabSolver(Solver):
+    """One slab of a multi-process run: one rank per GPU, NCCL between x-neighbours."""
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, PBF_COMM_ID_BYTES)
+        self._check(self.lib.pbf_comm_init(self.ctx, rank, nranks, buf))
+
+    def slab_upload(self, state6):
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in state6]
+        self._check(self.lib.pbf_slab_upload(self.ctx, arrs[0].shape[0], *[fptr(a) for a in arrs]))
+
+    def slab_upload_owned(self, gid, state6):
+        gid = np.ascontiguousarray(gid, dtype=np.int64)
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in state6]
+        self._check(self.lib.pbf_slab_upload_owned(self.ctx, gid.shape[0], gid.ctypes.data_as(_i64p),
+                                                   *[fptr(a) for a in arrs]))
+
+    def owned(self) -> int:
+        return int(self.lib.pbf_slab_owned(self.ctx))
+
+    def cuts(self):
+        lo, hi = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self._check(self.lib.pbf_slab_cuts(self.ctx, iptr(lo), iptr(hi)))
+        return int(lo[0]), int(hi[0])
+
+    def slab_download(self):
+        n = self.owned()
+        gid = np.empty(n, dtype=np.int64)
+        out = [np.empty(n, dtype=np.float32) for _ in range(6)]
+        self._check(self.lib.pbf_slab_download(self.ctx, gid.ctypes.data_as(_i64p), *[fptr(a) for a in out]))
+        return gid, out
+
+    def slab_stats(self) -> dict:
+        ex, by = C.c_uint64(0), C.c_uint64(0)
+        gh, hops = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self._check(self.lib.pbf_slab_stats(self.ctx, C.byref(ex), C.byref(by), iptr(gh), iptr(hops)))
+        return {"exchanges": int(ex.value), "bytes_sent": int(by.value), "ghosts": int(gh[0]), "hops": int(hops[0])}
+
+
+class SlabGroup:
+    """Several slabs driven by ONE process (pbf_group_*): contexts on the same device are
+    "virtual ranks" (the 1-GPU parity tests), contexts on different devices a single-process
+    multi-GPU run."""
+
+    def __init__(self, devices, params: PbfParams, planes: np.ndarray, mode: int = PBF_MODE_STRICT):
+        self.lib = load_library()
+        self.slabs = [SlabSolver(d, 0, mode) for d in devices]
+        for s in self.slabs:
+            s.set_params(params)
+            s.set_planes(planes)
+        arr = (C.c_void_p * len(self.slabs))(*[s.ctx for s in self.slabs])
+        self.group = self.lib.pbf_group_create(arr, len(self.slabs))
+        if not self.group:
+            raise PbfError("pbf_group_create failed")
+        self.n = 0
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msgs = [(self.lib.pbf_last_error(s.ctx) or b"").decode() for s in self.slabs]
+            raise PbfError(f"pbf group error {rc}: {[m for m in msgs if m]}")
+
+    def upload(self, state6):
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in state6]
+        self.n = arrs[0].shape[0]
+        self._check(self.lib.pbf_group_upload(self.group, self.n, *[fptr(a) for a in arrs]))
+
+    def step(self, nsteps: int = 1):
+        self._check(self.lib.pbf_group_step(self.group, nsteps))
+
+    def download(self):
+        out = [np.empty(self.n, dtype=np.float32) for _ in range(6)]
+        self._check(self.lib.pbf_group_download(self.group, *[fptr(a) for a in out]))
+        return out
+
+    def owned(self):
+        return [s.owned() for s in self.slabs]
+
+    def close(self):
+        if getattr(self, "group", None):
+            self.lib.pbf_group_destroy(self.group)
+            self.group = None
+        for s in getattr(self, "slabs", []):
+            s.close()
+        self.slabs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

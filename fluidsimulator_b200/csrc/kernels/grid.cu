@@ -26,10 +26,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ bool batch_failed(const StatusBlock* st) {
-  return (st->grid_overflow | st->nbr_overflow) != 0;
-}
-
 // ---------------------------------------------------------------- state (de)interleave
 __global__ void __launch_bounds__(kThreads)
 k_pack_state(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
@@ -62,8 +58,9 @@ k_unpack_state(const float4* __restrict__ pos_o, const float4* __restrict__ vel_
 // coordinates.  Grid-stride so that only a few thousand warps touch the six atomics.
 __global__ void __launch_bounds__(kThreads)
 k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
-          float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, int n) {
+          float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, NRef nr, int do_bounds) {
   if (batch_failed(st)) return;
+  const int n = nr.get();
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX};
   int hi[3] = {INT_MIN, INT_MIN, INT_MIN};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -81,6 +78,7 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
     lo[1] = min(lo[1], cy); hi[1] = max(hi[1], cy);
     lo[2] = min(lo[2], cz); hi[2] = max(hi[2], cz);
   }
+  if (!do_bounds) return;  // slab mode: the bounds are taken after migration (k_slab_merge)
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int wlo = __reduce_min_sync(0xffffffffu, lo[a]);
@@ -94,13 +92,18 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
 }
 
 // One thread: bounds -> GridDesc, capacity check, reset of the running bounds.
-__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap) {
+// `pad` empty layers surround the occupied cells: 1 so the 27-cell stencil of every particle stays
+// inside the table; 2 in slab mode, where first-layer ghosts run their own stencil.
+__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad) {
   if (batch_failed(st)) return;
   unsigned long long cells = 1;
   bool bad = false;
+  // a slab that currently owns no particle (everything migrated away) keeps a minimal table
+  const bool empty = st->min_cell[0] == INT_MAX && st->max_cell[0] == INT_MIN;
   for (int a = 0; a < 3; ++a) {
-    const long long lo = (long long)st->min_cell[a] - 1;
-    const long long hi = (long long)st->max_cell[a] + 1;
+    if (empty) st->min_cell[a] = st->max_cell[a] = 0;
+    const long long lo = (long long)st->min_cell[a] - pad;
+    const long long hi = (long long)st->max_cell[a] + pad;
     const long long dim = hi - lo + 1;
     if (st->min_cell[a] == INT_MIN || st->max_cell[a] == INT_MIN || dim <= 0 || dim > 0x7fffffffLL) bad = true;
     desc->lo[a] = (int)lo;
@@ -113,7 +116,11 @@ __global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_c
     st->max_cell[a] = INT_MIN;
   }
   if (bad) cells = 0xffffffffffffULL;
-  if (cells > st->max_cells) st->max_cells = cells;
+  const unsigned long long seen = ((unsigned long long)st->max_cells_hi << 32) | st->max_cells_lo;
+  if (cells > seen) {
+    st->max_cells_hi = (unsigned int)(cells >> 32);
+    st->max_cells_lo = (unsigned int)cells;
+  }
   const int overflow = (cells > (unsigned long long)cell_cap) ? 1 : 0;
   desc->ncells = overflow ? 0u : (uint32_t)cells;
   desc->overflow = overflow;
@@ -131,9 +138,10 @@ __device__ __forceinline__ uint32_t dense_key(float4 q, float inv_h, const GridD
 // keys in ORIGINAL particle order + the per-block digit histogram of radix pass 0.
 __global__ void __launch_bounds__(kThreads)
 k_keys_hist(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist,
-            float inv_h, const GridDesc* __restrict__ desc, const StatusBlock* st, int n, int nblocks) {
+            float inv_h, const GridDesc* __restrict__ desc, const StatusBlock* st, NRef nr, int nblocks) {
   __shared__ uint32_t sh[kRadixBins];
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const GridDesc d = *desc;
   for (int b = threadIdx.x; b < kRadixBins; b += kThreads) sh[b] = 0;
   __syncthreads();
@@ -153,9 +161,10 @@ k_keys_hist(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint
 
 __global__ void __launch_bounds__(kThreads)
 k_radix_hist(const uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, const StatusBlock* st,
-             int n, int nblocks, int shift) {
+             NRef nr, int nblocks, int shift) {
   __shared__ uint32_t sh[kRadixBins];
   if (batch_failed(st)) return;
+  const int n = nr.get();
   for (int b = threadIdx.x; b < kRadixBins; b += kThreads) sh[b] = 0;
   __syncthreads();
   const int base = blockIdx.x * kSortTile;
@@ -257,12 +266,13 @@ __global__ void __launch_bounds__(kThreads)
 k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ chunk_total,
-                const StatusBlock* st, int n, int nblocks, int shift) {
+                const StatusBlock* st, NRef nr, int nblocks, int shift) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kRounds = kSortTile / kThreads;  // per warp: kRounds x 32 consecutive keys
   __shared__ uint32_t whist[kWarps][kRadixBins];
   __shared__ uint32_t digit_base[kRadixBins];
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b = threadIdx.x; b < kWarps * kRadixBins; b += kThreads) (&whist[0][0])[b] = 0;
   // global base of (digit, this block) = in-chunk exclusive scan + sum of the earlier chunk totals
@@ -329,8 +339,9 @@ __global__ void __launch_bounds__(kThreads)
 k_cells_reorder(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                 const float4* __restrict__ pred_o, const float4* __restrict__ pos_o,
                 float4* __restrict__ pred_s, float4* __restrict__ pos_s,
-                int2* __restrict__ cell_range, const StatusBlock* st, int n) {
+                int2* __restrict__ cell_range, const StatusBlock* st, NRef nr) {
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t k = keys[i];
@@ -353,16 +364,27 @@ k_cells_reorder(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
             const GridDesc* __restrict__ desc, uint32_t* __restrict__ nbr_idx,
-            uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2, int K, int n) {
+            uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2, int K, NRef nr) {
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t cnt = 0;
-  if (i < n) {
-    const float4 pi = pred_s[i];
-    const int dimy = desc->dim[1], dimz = desc->dim[2];
-    const int cx = cell_coord(pi.x, inv_h) - desc->lo[0];
-    const int cy = cell_coord(pi.y, inv_h) - desc->lo[1];
-    const int cz = cell_coord(pi.z, inv_h) - desc->lo[2];
+  bool active = i < n;
+  int cx = 0, cy = 0, cz = 0;
+  float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int dimy = desc->dim[1], dimz = desc->dim[2];
+  if (active) {
+    pi = pred_s[i];
+    // Owned particles always sit at least one layer inside the table.  Ghosts of the outermost
+    // layer (or outside the table) can not touch an owned particle: they get an empty list.
+    const long long rx = (long long)cell_coord(pi.x, inv_h) - desc->lo[0];
+    const long long ry = (long long)cell_coord(pi.y, inv_h) - desc->lo[1];
+    const long long rz = (long long)cell_coord(pi.z, inv_h) - desc->lo[2];
+    active = rx >= 1 && rx <= desc->dim[0] - 2 && ry >= 1 && ry <= dimy - 2 && rz >= 1 && rz <= dimz - 2;
+    cx = (int)rx; cy = (int)ry; cz = (int)rz;
+    if (!active) nbr_count[i] = 0;
+  }
+  if (active) {
     uint32_t* out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
     const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
     const f2 xi = bcast(pi.x), yi = bcast(pi.y), zi = bcast(pi.z);
@@ -431,18 +453,24 @@ int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const s
 }
 
 int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConsts& c,
-                   const GridBuffers& g, int n, cudaStream_t s) {
-  int blocks = grid_for(n, kThreads);
+                   const GridBuffers& g, NRef n, bool slab, cudaStream_t s) {
+  int blocks = grid_for(n.n, kThreads);
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_begin_substep<<<1, 1, 0, s>>>(g.status);
-  k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n);
-  k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap);
+  k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n, slab ? 0 : 1);
+  if (slab) return 2;  // bounds + table descriptor follow the migration (launch_grid_finalize)
+  k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap, 1);
   return 3;
 }
 
-int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, int n, int* out,
+int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s) {
+  k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap, pad);
+  return 1;
+}
+
+int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, NRef n, int* out,
                 cudaStream_t s) {
-  const int nblocks = sort_blocks(n);
+  const int nblocks = sort_blocks(n.n);
   const int m = kRadixBins * nblocks;
   int launches = 0;
   int cur = 0;
@@ -467,17 +495,17 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
 
 int launch_cells_reorder(const uint32_t* keys, const uint32_t* vals, const float4* pred_o,
                          const float4* pos_o, float4* pred_s, float4* pos_s, const GridBuffers& g,
-                         int n, cudaStream_t s) {
+                         NRef n, cudaStream_t s) {
   k_clear_cells<<<148 * 4, kThreads, 0, s>>>(g.cell_range, g.desc, g.status);
-  k_cells_reorder<<<grid_for(n, kThreads), kThreads, 0, s>>>(keys, vals, pred_o, pos_o, pred_s, pos_s,
-                                                            g.cell_range, g.status, n);
+  k_cells_reorder<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(keys, vals, pred_o, pos_o, pred_s, pos_s,
+                                                              g.cell_range, g.status, n);
   return 2;
 }
 
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,
-                     const NeighborList& nl, int n, cudaStream_t s) {
-  k_neighbors<<<grid_for(n, 128), 128, 0, s>>>(pred_s, g.cell_range, g.desc, nl.idx, nl.count, g.status,
-                                              c.inv_h, c.h2, nl.K, n);
+                     const NeighborList& nl, NRef n, cudaStream_t s) {
+  k_neighbors<<<grid_for(n.n, 128), 128, 0, s>>>(pred_s, g.cell_range, g.desc, nl.idx, nl.count, g.status,
+                                                c.inv_h, c.h2, nl.K, n);
   return 1;
 }
 

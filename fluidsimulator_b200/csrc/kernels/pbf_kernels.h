@@ -39,20 +39,21 @@ int launch_pack_state(const float* const soa[6], float4* pos_o, float4* vel_o, i
 int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const soa[6], int n, cudaStream_t s);
 
 // a3+a4: integrate, predicted positions, cell bounds (always STRICT arithmetic: the
-// grid tables are bit-exact in both modes).
+// grid tables are bit-exact in both modes).  slab: bounds are taken after migration instead.
 int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConsts& c,
-                   const GridBuffers& g, int n, cudaStream_t s);
+                   const GridBuffers& g, NRef n, bool slab, cudaStream_t s);
+int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s);
 // a4+a5: dense keys + LSD radix sort (stable => ties keep ascending particle id).
 // On return the sorted keys/vals are in g.keys[out]/g.vals[out]; returns launches, sets *out.
-int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, int n,
+int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, NRef n,
                 int* out, cudaStream_t s);
 // a6 + reorder: dense cell start/end table, gather pred/pos into sorted order.
 int launch_cells_reorder(const uint32_t* keys, const uint32_t* vals, const float4* pred_o,
                          const float4* pos_o, float4* pred_s, float4* pos_s,
-                         const GridBuffers& g, int n, cudaStream_t s);
+                         const GridBuffers& g, NRef n, cudaStream_t s);
 // a7: neighbour list in the oracle's traversal order.
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,
-                     const NeighborList& nl, int n, cudaStream_t s);
+                     const NeighborList& nl, NRef n, cudaStream_t s);
 
 struct SolveBuffers {
   float4* pred[2];   // ping-pong (pred xyz, lambda)
@@ -72,7 +73,57 @@ struct SolveBuffers {
 // stage_cb (may be null) is invoked between stages for profiling.
 typedef void (*StageCallback)(void* user, int stage_id, int begin);
 int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c,
-                 int iterations, int n, bool strict, cudaStream_t s,
+                 int iterations, NRef n, bool strict, cudaStream_t s,
                  StageCallback cb, void* cb_user);
+// The individual passes (the slab driver puts halo exchanges between them).  `cur` selects the
+// pred ping-pong buffer a pass reads; delta writes pred[cur ^ 1].
+int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
+                  bool strict, cudaStream_t s);
+int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
+                 bool is_final, NRef n, bool strict, cudaStream_t s);
+int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,
+                NRef n, bool strict, cudaStream_t s);
+int launch_vort_omega(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
+                      NRef n, bool strict, cudaStream_t s);
+int launch_vort_apply(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
+                      NRef n, bool strict, cudaStream_t s);
+int launch_commit_only(const SolveBuffers& b, const StepConsts& c, NRef n, bool strict, cudaStream_t s);
+
+// ---- x-slab decomposition (kernels/slab.cu) --------------------------------------
+// Messages between x-neighbours are fixed-capacity float4 arrays; element 0 is a header whose .x
+// holds the element count as bits.
+struct SlabBuffers {
+  SlabCounts* counts;       // device
+  StatusBlock* status;
+  uint32_t* gid_o;          // global particle id per owned slot (ascending)
+  float4 *keep_pos, *keep_pred;  // staging of the particles that stay (pos.w = bits(gid))
+  uint32_t* blk_cnt;        // 3 * blocks(cap) class counters
+  float4* send[2];          // message to the left / right neighbour
+  float4* recv[2];          // message from the left / right neighbour
+  int cut_lo, cut_hi;       // owned x-cells [cut_lo, cut_hi); INT_MIN / INT_MAX at the ends
+  int cap;                  // owned-particle capacity
+  int tot_cap;              // capacity of the sorted arrays (owned + ghosts)
+  int mcap;                 // migration message capacity (particles)
+  int gcap;                 // ghost message capacity (particles)
+};
+// migration, one hop: classify by predicted x-cell, stable 3-way split, pack the two messages
+int launch_slab_split(const float4* pos_o, const float4* pred_o, const SlabBuffers& sb, const StepConsts& c,
+                      cudaStream_t s);
+// merge kept + received particles by ascending global id into pos_o/pred_o/gid_o; on the last hop
+// also takes the cell bounds and flags particles that are still outside the slab
+int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, bool last_hop,
+                      cudaStream_t s);
+// boundary counts + ghost messages (pred, pos of the two boundary layers on each side)
+int launch_slab_ghost_pack(const uint32_t* keys_sorted, const float4* pred_s, const float4* pos_s,
+                           const GridBuffers& g, const SlabBuffers& sb, cudaStream_t s);
+// append received ghosts after the owned slots and insert their cells into the table
+int launch_slab_ghost_unpack(float4* pred_s, float4* pos_s, const GridBuffers& g, const SlabBuffers& sb,
+                             const StepConsts& c, cudaStream_t s);
+// per-iteration refresh of one float4 array: boundary slots -> messages, messages -> ghost slots
+int launch_slab_halo_pack(const float4* arr, const SlabBuffers& sb, cudaStream_t s);
+int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s);
+// ghost velocities (pred - pos)/dt and m/rho, recomputed locally after the last pred refresh
+int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel,
+                          const SlabBuffers& sb, const StepConsts& c, bool strict, cudaStream_t s);
 
 }  // namespace pbf

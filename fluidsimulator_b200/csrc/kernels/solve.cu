@@ -43,10 +43,6 @@ constexpr int kPairUnroll = PBF_PAIR_UNROLL;  // neighbour PAIRS fetched per bat
 template <bool S> using FT = typename std::conditional<S, sfloat, float>::type;
 template <typename F> struct V3 { F x, y, z; };
 
-__device__ __forceinline__ bool batch_failed(const StatusBlock* st) {
-  return (st->grid_overflow | st->nbr_overflow) != 0;
-}
-
 // ---- pair iteration -----------------------------------------------------------------
 // Walks the list of sorted slot i.  Full pairs run without any validity logic; an odd count
 // ends with one half-valid pair.  body(a0, a1, v1): data of the two neighbours and validity of the second.
@@ -206,10 +202,11 @@ template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
-         const StatusBlock* st, DebugPtrs dbg, int K, int n) {
+         const StatusBlock* st, DebugPtrs dbg, int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pred[i];
@@ -261,10 +258,11 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
         const float4* __restrict__ pos_s, const float* __restrict__ rho, float4* __restrict__ vel_out,
         const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
-        StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final, int K, int n) {
+        StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final, int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pred_in[i];
@@ -342,10 +340,11 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
        const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
        const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
        float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final,
-       int K, int n) {
+       int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pos[i];
@@ -388,10 +387,11 @@ template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* __restrict__ omega,
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count, StepConsts c,
-             const StatusBlock* st, int K, int n) {
+             const StatusBlock* st, int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pos[i];
@@ -433,10 +433,11 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
              const float4* __restrict__ pos_s, const float4* __restrict__ planes,
              float4* __restrict__ pos_o, float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st,
-             DebugPtrs dbg, int K, int n) {
+             DebugPtrs dbg, int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 pi = pos[i];
@@ -482,64 +483,15 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   finalize_particle<F>(pi, v, __float_as_uint(pos_s[i].w), c, planes, pos_o, vel_o);
 }
 
-template <bool S>
-int solve_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int iterations, int n,
-               cudaStream_t s, StageCallback cb, void* user) {
-  const int blocks = (n + kBlock - 1) / kBlock;
-  int launches = 0;
-  int cur = 0;
-  auto stage = [&](int id, int begin) { if (cb) cb(user, id, begin); };
-  const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
-  const int final_in_delta = (!tail_xsph && !tail_vort) ? 1 : 0;
-  for (int it = 0; it < iterations; ++it) {
-    const bool last = (it == iterations - 1);
-    stage(4, 1);
-    k_lambda<S><<<blocks, kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
-    stage(4, 0);
-    stage(5, 1);
-    if (last)
-      k_delta<S, true><<<blocks, kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                 b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg,
-                                                 final_in_delta, nl.K, n);
-    else
-      k_delta<S, false><<<blocks, kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                  b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, 0,
-                                                  nl.K, n);
-    stage(5, 0);
-    cur ^= 1;
-    launches += 2;
-  }
-  float4* pos = b.pred[cur];  // committed positions, sorted order
-  int vcur = 0;
-  if (tail_xsph) {
-    stage(6, 1);
-    k_xsph<S><<<blocks, kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
-                                        b.vel_o, c, b.status, b.dbg, tail_vort ? 0 : 1, nl.K, n);
-    stage(6, 0);
-    vcur = 1;
-    ++launches;
-  }
-  if (tail_vort) {
-    stage(7, 1);
-    k_vort_omega<S><<<blocks, kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
-    stage(7, 0);
-    stage(8, 1);
-    k_vort_apply<S><<<blocks, kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
-                                              b.pos_o, b.vel_o, c, b.status, b.dbg, nl.K, n);
-    stage(8, 0);
-    launches += 2;
-  }
-  return launches;
-}
-
 // solver_iterations == 0: core.cpp:277 never runs, pred is committed as predicted.
 template <bool S>
 __global__ void __launch_bounds__(kBlock)
 k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
               const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
-              StepConsts c, const StatusBlock* st, int n) {
+              StepConsts c, const StatusBlock* st, NRef nr) {
   using F = FT<S>;
   if (batch_failed(st)) return;
+  const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 np = pred[i];
@@ -553,23 +505,118 @@ k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
 
 }  // namespace
 
-int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int iterations, int n,
-                 bool strict, cudaStream_t s, StageCallback cb, void* cb_user) {
-  if (iterations <= 0) {
-    // rho/lambda are never computed in this case (the reference reads its stale scratch);
-    // XSPH would need rho, so only the plain commit is supported.
-    const int blocks = (n + kBlock - 1) / kBlock;
-    StepConsts c0 = c;
-    c0.do_xsph = 0;
-    c0.do_vort = 0;
-    if (strict)
-      k_commit_only<true><<<blocks, kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
-    else
-      k_commit_only<false><<<blocks, kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
-    return 1;
+// ---- per-pass launchers (the slab driver interleaves them with halo exchanges) ----------------
+static inline int blocks_for(NRef n) { return (n.n + kBlock - 1) / kBlock; }
+
+int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
+                  bool strict, cudaStream_t s) {
+  if (strict)
+    k_lambda<true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+  else
+    k_lambda<false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+  return 1;
+}
+
+template <bool S>
+static void delta_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
+                       bool is_final, NRef n, cudaStream_t s) {
+  if (last)
+    k_delta<S, true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
+                                                     b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg,
+                                                     is_final ? 1 : 0, nl.K, n);
+  else
+    k_delta<S, false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
+                                                      b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, 0,
+                                                      nl.K, n);
+}
+
+int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
+                 bool is_final, NRef n, bool strict, cudaStream_t s) {
+  if (strict) delta_impl<true>(b, nl, c, cur, last, is_final, n, s);
+  else delta_impl<false>(b, nl, c, cur, last, is_final, n, s);
+  return 1;
+}
+
+int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,
+                NRef n, bool strict, cudaStream_t s) {
+  if (strict)
+    k_xsph<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
+                                                 b.vel_o, c, b.status, b.dbg, is_final ? 1 : 0, nl.K, n);
+  else
+    k_xsph<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
+                                                  b.vel_o, c, b.status, b.dbg, is_final ? 1 : 0, nl.K, n);
+  return 1;
+}
+
+int launch_vort_omega(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
+                      NRef n, bool strict, cudaStream_t s) {
+  if (strict)
+    k_vort_omega<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
+  else
+    k_vort_omega<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
+  return 1;
+}
+
+int launch_vort_apply(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
+                      NRef n, bool strict, cudaStream_t s) {
+  if (strict)
+    k_vort_apply<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
+                                                       b.pos_o, b.vel_o, c, b.status, b.dbg, nl.K, n);
+  else
+    k_vort_apply<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
+                                                        b.pos_o, b.vel_o, c, b.status, b.dbg, nl.K, n);
+  return 1;
+}
+
+int launch_commit_only(const SolveBuffers& b, const StepConsts& c, NRef n, bool strict, cudaStream_t s) {
+  // rho/lambda are never computed when solver_iterations == 0 (the reference reads its stale
+  // scratch); XSPH would need rho, so only the plain commit is supported.
+  StepConsts c0 = c;
+  c0.do_xsph = 0;
+  c0.do_vort = 0;
+  if (strict)
+    k_commit_only<true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
+  else
+    k_commit_only<false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
+  return 1;
+}
+
+// a8..a14 of one substep on a single GPU.
+int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int iterations, NRef n,
+                 bool strict, cudaStream_t s, StageCallback cb, void* user) {
+  if (iterations <= 0) return launch_commit_only(b, c, n, strict, s);
+  int launches = 0;
+  int cur = 0;
+  auto stage = [&](int id, int begin) { if (cb) cb(user, id, begin); };
+  const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
+  const bool final_in_delta = !tail_xsph && !tail_vort;
+  for (int it = 0; it < iterations; ++it) {
+    const bool last = (it == iterations - 1);
+    stage(4, 1);
+    launches += launch_lambda(b, nl, c, cur, n, strict, s);
+    stage(4, 0);
+    stage(5, 1);
+    launches += launch_delta(b, nl, c, cur, last, last && final_in_delta, n, strict, s);
+    stage(5, 0);
+    cur ^= 1;
   }
-  return strict ? solve_impl<true>(b, nl, c, iterations, n, s, cb, cb_user)
-                : solve_impl<false>(b, nl, c, iterations, n, s, cb, cb_user);
+  float4* pos = b.pred[cur];  // committed positions, sorted order
+  int vcur = 0;
+  if (tail_xsph) {
+    stage(6, 1);
+    launches += launch_xsph(b, nl, c, pos, !tail_vort, n, strict, s);
+    stage(6, 0);
+    vcur = 1;
+  }
+  if (tail_vort) {
+    stage(7, 1);
+    launches += launch_vort_omega(b, nl, c, pos, vcur, n, strict, s);
+    stage(7, 0);
+    stage(8, 1);
+    launches += launch_vort_apply(b, nl, c, pos, vcur, n, strict, s);
+    stage(8, 0);
+  }
+  return launches;
 }
 
 }  // namespace pbf

@@ -14,20 +14,17 @@
 using namespace pbf;
 
 namespace {
-
 thread_local std::string g_error;  // context-less failures (pbf_create, pbf_device_count)
+}
 
+namespace pbf {
 int fail(pbf_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->error = msg; else g_error = msg;
   return code;
 }
+}  // namespace pbf
 
-#define PBF_CUDA(ctx, expr)                                                                  \
-  do {                                                                                       \
-    cudaError_t _e = (expr);                                                                 \
-    if (_e != cudaSuccess)                                                                   \
-      return fail(ctx, PBF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
-  } while (0)
+namespace {
 
 constexpr float kPi = 3.14159265358979323846f;  // core.cpp:10
 
@@ -90,6 +87,10 @@ StepConsts make_consts(const pbf_params& p, int nplanes) {
   return c;
 }
 
+}  // namespace
+
+namespace pbf {
+
 int sort_passes_for(uint32_t cell_cap) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < (unsigned long long)cell_cap) ++bits;
@@ -103,31 +104,44 @@ void invalidate_graph(pbf_ctx* ctx) {
   }
 }
 
-int ensure_particles(pbf_ctx* ctx, size_t n) {
-  if (n <= ctx->cap) return PBF_OK;
-  const size_t cap = std::max<size_t>(n, 1024);
+// Per-particle buffers.  Arrays in ORIGINAL order hold `cap` owned particles; arrays in SORTED order
+// additionally hold the ghosts of a slab (tot = cap + 2 * gcap; gcap == 0 on a single GPU).
+// `keep` > 0 preserves that many elements of the persistent state across the growth.
+int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep) {
+  const size_t want_tot = std::max<size_t>(n, 1024) + 2 * (size_t)ctx->slab.gcap;
+  if (n <= ctx->cap && want_tot <= ctx->pred_a.n) return PBF_OK;
+  const size_t cap = std::max<size_t>(std::max<size_t>(n, 1024), ctx->cap);
+  const size_t tot = cap + 2 * (size_t)ctx->slab.gcap;
   invalidate_graph(ctx);
-  PBF_CUDA(ctx, ctx->pos_o.reserve(cap));
-  PBF_CUDA(ctx, ctx->vel_o.reserve(cap));
-  PBF_CUDA(ctx, ctx->pos_bak.reserve(cap));
-  PBF_CUDA(ctx, ctx->vel_bak.reserve(cap));
+  PBF_CUDA(ctx, ctx->pos_o.grow_keep(cap, keep));
+  PBF_CUDA(ctx, ctx->vel_o.grow_keep(cap, keep));
+  PBF_CUDA(ctx, ctx->pos_bak.grow_keep(cap, keep));
+  PBF_CUDA(ctx, ctx->vel_bak.grow_keep(cap, keep));
   PBF_CUDA(ctx, ctx->pred_o.reserve(cap));
-  PBF_CUDA(ctx, ctx->pred_a.reserve(cap));
-  PBF_CUDA(ctx, ctx->pred_b.reserve(cap));
-  PBF_CUDA(ctx, ctx->pos_s.reserve(cap));
-  PBF_CUDA(ctx, ctx->vel_a.reserve(cap));
-  PBF_CUDA(ctx, ctx->vel_b.reserve(cap));
-  PBF_CUDA(ctx, ctx->omega.reserve(cap));
-  PBF_CUDA(ctx, ctx->rho.reserve(cap));
+  PBF_CUDA(ctx, ctx->pred_a.reserve(tot));
+  PBF_CUDA(ctx, ctx->pred_b.reserve(tot));
+  PBF_CUDA(ctx, ctx->pos_s.reserve(tot));
+  PBF_CUDA(ctx, ctx->vel_a.reserve(tot));
+  PBF_CUDA(ctx, ctx->vel_b.reserve(tot));
+  PBF_CUDA(ctx, ctx->omega.reserve(tot));
+  PBF_CUDA(ctx, ctx->rho.reserve(tot));
   PBF_CUDA(ctx, ctx->keys0.reserve(cap));
   PBF_CUDA(ctx, ctx->keys1.reserve(cap));
   PBF_CUDA(ctx, ctx->vals0.reserve(cap));
   PBF_CUDA(ctx, ctx->vals1.reserve(cap));
   PBF_CUDA(ctx, ctx->hist.reserve((size_t)kRadixBins * sort_blocks((int)cap)));
   PBF_CUDA(ctx, ctx->chunk_total.reserve((size_t)kRadixBins * sort_blocks((int)cap) / 2048 + 2));
-  PBF_CUDA(ctx, ctx->nbr_count.reserve(cap));
+  PBF_CUDA(ctx, ctx->nbr_count.reserve(tot));
   for (auto& b : ctx->soa) PBF_CUDA(ctx, b.reserve(cap));
+  if (ctx->slab.enabled) {
+    PBF_CUDA(ctx, ctx->slab.gid_o.grow_keep(cap, keep));
+    PBF_CUDA(ctx, ctx->slab.gid_bak.grow_keep(cap, keep));
+    PBF_CUDA(ctx, ctx->slab.keep_pos.reserve(cap));
+    PBF_CUDA(ctx, ctx->slab.keep_pred.reserve(cap));
+    PBF_CUDA(ctx, ctx->slab.blk_cnt.reserve(3 * ((cap + 255) / 256) + 3));
+  }
   ctx->cap = cap;
+  ctx->slab.tot_cap = ctx->slab.enabled ? tot : 0;
   return PBF_OK;
 }
 
@@ -136,17 +150,18 @@ int ensure_tables(pbf_ctx* ctx) {
     invalidate_graph(ctx);
     PBF_CUDA(ctx, ctx->cell_range.reserve(ctx->cell_cap));
   }
-  const size_t need = ((ctx->cap + 31) / 32) * (size_t)ctx->K * 32u;
+  const size_t slots = ctx->slab.enabled ? ctx->slab.tot_cap : ctx->cap;
+  const size_t need = ((slots + 31) / 32) * (size_t)ctx->K * 32u;
   if (ctx->nbr_idx.n < need) {
     invalidate_graph(ctx);
     PBF_CUDA(ctx, ctx->nbr_idx.reserve(need));
   }
   if (ctx->debug) {
-    PBF_CUDA(ctx, ctx->dbg_lambda.reserve(ctx->cap));
-    PBF_CUDA(ctx, ctx->dbg_rho.reserve(ctx->cap));
-    PBF_CUDA(ctx, ctx->dbg_delta.reserve(ctx->cap));
-    PBF_CUDA(ctx, ctx->dbg_dv.reserve(ctx->cap));
-    PBF_CUDA(ctx, ctx->dbg_eta.reserve(ctx->cap));
+    PBF_CUDA(ctx, ctx->dbg_lambda.reserve(slots));
+    PBF_CUDA(ctx, ctx->dbg_rho.reserve(slots));
+    PBF_CUDA(ctx, ctx->dbg_delta.reserve(slots));
+    PBF_CUDA(ctx, ctx->dbg_dv.reserve(slots));
+    PBF_CUDA(ctx, ctx->dbg_eta.reserve(slots));
   }
   return PBF_OK;
 }
@@ -162,10 +177,6 @@ cudaEvent_t timer_event(StageTimer& t) {
   cudaEventCreate(&e);
   return e;
 }
-
-struct StageCtx {
-  pbf_ctx* ctx;
-};
 
 void stage_mark(void* user, int stage, int begin) {
   pbf_ctx* ctx = static_cast<pbf_ctx*>(user);
@@ -196,10 +207,7 @@ void timer_resolve(pbf_ctx* ctx) {
 
 // ---- one substep ------------------------------------------------------------
 // Enqueues the kernels of one substep.  Returns the kernel count.
-int enqueue_substep(pbf_ctx* ctx) {
-  const int n = (int)ctx->n;
-  cudaStream_t s = ctx->stream;
-  GridBuffers g{};
+void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g) {
   g.desc = ctx->desc.p;
   g.status = ctx->status.p;
   g.keys[0] = ctx->keys0.p;
@@ -211,13 +219,41 @@ int enqueue_substep(pbf_ctx* ctx) {
   g.cell_range = ctx->cell_range.p;
   g.cell_cap = ctx->cell_cap;
   g.sort_passes = sort_passes_for(ctx->cell_cap);
+}
+
+void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
+  b.pred[0] = ctx->pred_a.p;
+  b.pred[1] = ctx->pred_b.p;
+  b.pos_s = ctx->pos_s.p;
+  b.vel[0] = ctx->vel_a.p;
+  b.vel[1] = ctx->vel_b.p;
+  b.omega = ctx->omega.p;
+  b.rho = ctx->rho.p;
+  b.planes = ctx->planes_dev.p;
+  b.pos_o = ctx->pos_o.p;
+  b.vel_o = ctx->vel_o.p;
+  b.status = ctx->status.p;
+  if (ctx->debug) {
+    b.dbg.lambda = ctx->dbg_lambda.p;
+    b.dbg.rho = ctx->dbg_rho.p;
+    b.dbg.delta = ctx->dbg_delta.p;
+    b.dbg.dv = ctx->dbg_dv.p;
+    b.dbg.eta = ctx->dbg_eta.p;
+  }
+}
+
+int enqueue_substep(pbf_ctx* ctx) {
+  const NRef n = nref((int)ctx->n);
+  cudaStream_t s = ctx->stream;
+  GridBuffers g{};
+  fill_grid_buffers(ctx, g);
   NeighborList nl{ctx->nbr_idx.p, ctx->nbr_count.p, ctx->K};
   const StepConsts& c = ctx->consts;
   StageTimer& t = ctx->timer;
   int launches = 0, k;
 
   stage_mark(ctx, PBF_STAGE_PREDICT, 1);
-  k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n, s);
+  k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n, false, s);
   stage_mark(ctx, PBF_STAGE_PREDICT, 0);
   t.launches[PBF_STAGE_PREDICT] += k; launches += k;
 
@@ -239,24 +275,7 @@ int enqueue_substep(pbf_ctx* ctx) {
   t.launches[PBF_STAGE_NEIGHBORS] += k; launches += k;
 
   SolveBuffers b{};
-  b.pred[0] = ctx->pred_a.p;
-  b.pred[1] = ctx->pred_b.p;
-  b.pos_s = ctx->pos_s.p;
-  b.vel[0] = ctx->vel_a.p;
-  b.vel[1] = ctx->vel_b.p;
-  b.omega = ctx->omega.p;
-  b.rho = ctx->rho.p;
-  b.planes = ctx->planes_dev.p;
-  b.pos_o = ctx->pos_o.p;
-  b.vel_o = ctx->vel_o.p;
-  b.status = ctx->status.p;
-  if (ctx->debug) {
-    b.dbg.lambda = ctx->dbg_lambda.p;
-    b.dbg.rho = ctx->dbg_rho.p;
-    b.dbg.delta = ctx->dbg_delta.p;
-    b.dbg.dv = ctx->dbg_dv.p;
-    b.dbg.eta = ctx->dbg_eta.p;
-  }
+  fill_solve_buffers(ctx, b);
   const int iters = ctx->params.solver_iterations;
   k = launch_solve(b, nl, c, iters, n, ctx->mode == PBF_MODE_STRICT, s, stage_mark, ctx);
   // attribute solver launches to their stages
@@ -271,6 +290,10 @@ int enqueue_substep(pbf_ctx* ctx) {
   launches += k;
   return launches;
 }
+
+}  // namespace pbf
+
+namespace {
 
 int run_substeps(pbf_ctx* ctx, int nsteps) {
   const bool graph = ctx->use_graph && !ctx->profile;
@@ -297,6 +320,10 @@ int run_substeps(pbf_ctx* ctx, int nsteps) {
   return PBF_OK;
 }
 
+}  // namespace
+
+namespace pbf {
+
 int reset_status(pbf_ctx* ctx) {
   StatusBlock z{};
   for (int a = 0; a < 3; ++a) { z.min_cell[a] = INT_MAX; z.max_cell[a] = INT_MIN; }
@@ -304,6 +331,10 @@ int reset_status(pbf_ctx* ctx) {
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status.p, ctx->status_host, sizeof(StatusBlock), cudaMemcpyHostToDevice, ctx->stream));
   return PBF_OK;
 }
+
+}  // namespace pbf
+
+namespace {
 
 template <typename T>
 int fetch(pbf_ctx* ctx, std::vector<T>& host, const T* dev, size_t count) {
@@ -381,7 +412,7 @@ pbf_ctx* pbf_create(int device, size_t capacity) {
     return nullptr;
   }
   ctx->stream = ctx->own_stream;
-  if (capacity > 0 && ensure_particles(ctx, capacity) != PBF_OK) {
+  if (capacity > 0 && ensure_particles(ctx, capacity, 0) != PBF_OK) {
     g_error = ctx->error;
     pbf_destroy(ctx);
     return nullptr;
@@ -403,6 +434,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
   ctx->dbg_dv.release(); ctx->dbg_eta.release();
+  slab_release(ctx);
   for (auto ev : ctx->timer.pool) cudaEventDestroy(ev);
   for (auto ev : ctx->timer.begin) cudaEventDestroy(ev);
   for (auto ev : ctx->timer.end) cudaEventDestroy(ev);
@@ -470,7 +502,8 @@ int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py, const f
   if (n > 0 && (!px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_upload: null array");
   if (n > 0x7fffffffu - 64) return fail(ctx, PBF_E_INVALID, "pbf_upload: more than 2^31 particles in one slab");
   cudaSetDevice(ctx->device);
-  int rc = ensure_particles(ctx, n);
+  if (ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_upload: this context is a slab; use pbf_slab_upload");
+  int rc = ensure_particles(ctx, n, 0);
   if (rc != PBF_OK) return rc;
   if (n != ctx->n) invalidate_graph(ctx);
   ctx->n = n;
@@ -504,6 +537,7 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
   if (!(ctx->params.h > 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_step: parameters not set (h == 0)");
   cudaSetDevice(ctx->device);
   if (nsteps == 0) return PBF_OK;
+  if (ctx->slab.enabled) return slab_step(ctx, nsteps);
   if (ctx->n == 0) {  // core.cpp:122-125: only time advances
     for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
     return PBF_OK;
@@ -532,16 +566,17 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     if (st.grid_overflow) {
-      if (st.max_cells > (1ull << 30)) {
+      const unsigned long long max_cells = ((unsigned long long)st.max_cells_hi << 32) | st.max_cells_lo;
+      if (max_cells > (1ull << 30)) {
         char buf[256];
         std::snprintf(buf, sizeof(buf),
                       "pbf_step: bounding grid needs %llu cells (> 2^30 dense-table limit); particle positions "
                       "have diverged or are non-finite (state restored to the start of the batch)",
-                      (unsigned long long)st.max_cells);
+                      max_cells);
         return fail(ctx, PBF_E_CAPACITY, buf);
       }
       uint32_t cap = ctx->cell_cap;
-      while ((unsigned long long)cap < st.max_cells + st.max_cells / 4) cap <<= 1;
+      while ((unsigned long long)cap < max_cells + max_cells / 4) cap <<= 1;
       ctx->cell_cap = cap;
       invalidate_graph(ctx);
     }

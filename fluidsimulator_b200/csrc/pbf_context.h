@@ -3,11 +3,14 @@
 
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <string>
 #include <vector>
 
 #include "kernels/pbf_kernels.h"
 #include "pbf_b200.h"
+
+struct pbf_ctx;
 
 namespace pbf {
 
@@ -24,11 +27,58 @@ struct DevBuf {
     if (e == cudaSuccess) n = count;
     return e;
   }
+  // grow, keeping the first `keep` elements (persistent state across a capacity change)
+  cudaError_t grow_keep(size_t count, size_t keep) {
+    if (count <= n) return cudaSuccess;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q), count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) e = cudaMemcpy(q, p, (keep < n ? keep : n) * sizeof(T), cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    p = q;
+    n = count;
+    return e;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
   }
+};
+
+// How one slab talks to its x-neighbours (pbf_slab.cu): NCCL between processes, or peer copies
+// between contexts of one process.
+struct Transport {
+  virtual ~Transport() {}
+  // send[0] -> left neighbour, send[1] -> right neighbour; recv[0] <- left, recv[1] <- right.
+  // `bytes` is the same on every rank.  Enqueued on the context's stream.
+  virtual int exchange(pbf_ctx* ctx, float4* const send[2], float4* const recv[2], size_t bytes) = 0;
+  // max-reduce the shared words of the device status block over all slabs (stream-ordered) ...
+  virtual int reduce_status_device(pbf_ctx* ctx, unsigned int* dev_words, int count) = 0;
+  // ... or of its host copy after the batch's synchronisation (whichever the transport supports)
+  virtual int reduce_status_host(pbf_ctx* ctx, unsigned int* host_words, int count) = 0;
+  virtual void abort() {}
+};
+
+struct SlabState {
+  bool enabled = false;
+  int rank = 0, nranks = 1;
+  int cut_lo = INT_MIN, cut_hi = INT_MAX;  // owned x-cells [cut_lo, cut_hi)
+  int mcap = 0, gcap = 0;                  // message capacities (particles)
+  int hops = 1;                            // migration hops per substep
+  size_t tot_cap = 0;                      // capacity of the sorted arrays (owned + ghosts)
+  size_t msg_elems = 0;                    // float4 elements per message buffer
+  int parity = 0;                          // which send buffer pair the next exchange uses
+  size_t n_bak = 0;                        // owned count at the start of the batch
+  uint64_t exchanges = 0;
+  uint64_t bytes_sent = 0;
+  Transport* transport = nullptr;          // not owned when it belongs to a group
+  bool owns_transport = false;
+  DevBuf<SlabCounts> counts;
+  DevBuf<uint32_t> gid_o, gid_bak, blk_cnt;
+  DevBuf<float4> keep_pos, keep_pred;
+  DevBuf<float4> send[2][2], recv[2];      // [parity][side], [side]
+  SlabCounts* counts_host = nullptr;       // pinned
 };
 
 struct StageTimer {
@@ -90,7 +140,33 @@ struct pbf_ctx {
   uint64_t graph_key = 0;
   int graph_kernels = 0;
 
+  pbf::SlabState slab;
+
   pbf::StageTimer timer;
   uint64_t launch_count = 0;
   uint64_t batches_retried = 0;
 };
+
+// ---- internals shared by pbf_capi.cu and pbf_slab.cu ---------------------------------------------
+#define PBF_CUDA(ctx, expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return pbf::fail(ctx, PBF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+namespace pbf {
+int fail(pbf_ctx* ctx, int code, const std::string& msg);
+int sort_passes_for(uint32_t cell_cap);
+void invalidate_graph(pbf_ctx* ctx);
+int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep);
+int ensure_tables(pbf_ctx* ctx);
+int reset_status(pbf_ctx* ctx);
+void stage_mark(void* user, int stage, int begin);
+void timer_resolve(pbf_ctx* ctx);
+void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g);
+void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b);
+// pbf_slab.cu
+int slab_step(pbf_ctx* ctx, int nsteps);
+void slab_release(pbf_ctx* ctx);
+}  // namespace pbf

@@ -1,32 +1,769 @@
-// pbf_slab.cu — x-slab decomposition across GPUs.  Placeholder entry points
-// until the halo-exchange path lands; they fail loudly rather than silently doing nothing.
+// pbf_slab.cu — host side of the x-slab decomposition: slab
+// planning, the two transports (NCCL between processes, peer copies inside one process), the
+// per-substep driver that interleaves the kernels of kernels/slab.cu with the solver passes, and
+// the C ABI around them.  The reference has no multi-GPU path; parity is pinned by requiring the
+// slab result to be bit-identical to the single-GPU result (tests/test_gpu_slabs.py).
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "pbf_context.h"
 
+using namespace pbf;
+
+// ================================================================== slab planning (host only)
+namespace {
+
+// static_cast<int>(std::floor(x * inv)) with inv = 1.0f / h — reference core.cpp:28-34; the
+// same expression the device uses (cell_coord in pbf_device.cuh).
+inline int host_cell(float x, float inv_h) {
+  const float f = std::floor(x * inv_h);
+  if (!(f >= -2147483648.0f && f < 2147483648.0f)) return INT_MIN;
+  return (int)f;
+}
+
+// Cuts on x-cell boundaries with (nearly) equal particle counts; every slab at least two cells
+// wide so that both ghost layers of a slab come from its direct neighbour.
+int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& cuts, std::string& err) {
+  cuts.assign((size_t)nranks + 1, 0);
+  cuts[0] = INT_MIN;
+  cuts[nranks] = INT_MAX;
+  if (nranks == 1) return PBF_OK;
+  if (n == 0) {
+    err = "slab plan: no particles";
+    return PBF_E_INVALID;
+  }
+  const float inv_h = 1.0f / h;
+  int lo = INT_MAX, hi = INT_MIN;
+  for (size_t i = 0; i < n; ++i) {
+    const int c = host_cell(px[i], inv_h);
+    lo = std::min(lo, c);
+    hi = std::max(hi, c);
+  }
+  const long long layers = (long long)hi - lo + 1;
+  if (lo == INT_MIN || layers < 2LL * nranks || layers > (1LL << 24)) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "slab plan: %lld x-layers of cells can not be split into %d slabs of >= 2 layers",
+                  layers, nranks);
+    err = buf;
+    return PBF_E_INVALID;
+  }
+  std::vector<size_t> hist((size_t)layers, 0);
+  for (size_t i = 0; i < n; ++i) hist[(size_t)(host_cell(px[i], inv_h) - lo)]++;
+  size_t cum = 0;
+  long long layer = 0;
+  for (int r = 1; r < nranks; ++r) {
+    const size_t target = (size_t)(((unsigned long long)n * (unsigned)r) / (unsigned)nranks);
+    const long long min_layer = (r == 1 ? 0 : (long long)cuts[r - 1] - lo) + 2;  // this slab >= 2 layers
+    const long long max_layer = layers - 2LL * (nranks - r);                      // room for the rest
+    while (layer < max_layer && (layer < min_layer || cum + hist[(size_t)layer] / 2 < target)) cum += hist[(size_t)layer++];
+    cuts[r] = (int)(lo + layer);
+  }
+  return PBF_OK;
+}
+
+}  // namespace
+
+// ================================================================== transports
+namespace {
+
+#define PBF_NCCL(ctx, expr)                                                                   \
+  do {                                                                                        \
+    ncclResult_t _r = (expr);                                                                 \
+    if (_r != ncclSuccess)                                                                    \
+      return fail(ctx, PBF_E_COMM, std::string(#expr) + ": " + ncclGetErrorString(_r));       \
+  } while (0)
+
+// One process per GPU: nearest-neighbour ncclSend/ncclRecv, grouped per exchange.
+struct NcclTransport : Transport {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  ~NcclTransport() override {
+    if (comm) ncclCommDestroy(comm);
+  }
+  int exchange(pbf_ctx* ctx, float4* const send[2], float4* const recv[2], size_t bytes) override {
+    if (nranks == 1) return PBF_OK;
+    PBF_NCCL(ctx, ncclGroupStart());
+    if (rank > 0) {
+      PBF_NCCL(ctx, ncclSend(send[0], bytes, ncclChar, rank - 1, comm, ctx->stream));
+      PBF_NCCL(ctx, ncclRecv(recv[0], bytes, ncclChar, rank - 1, comm, ctx->stream));
+    }
+    if (rank + 1 < nranks) {
+      PBF_NCCL(ctx, ncclSend(send[1], bytes, ncclChar, rank + 1, comm, ctx->stream));
+      PBF_NCCL(ctx, ncclRecv(recv[1], bytes, ncclChar, rank + 1, comm, ctx->stream));
+    }
+    PBF_NCCL(ctx, ncclGroupEnd());
+    return PBF_OK;
+  }
+  int reduce_status_device(pbf_ctx* ctx, unsigned int* dev_words, int count) override {
+    if (nranks == 1) return PBF_OK;
+    PBF_NCCL(ctx, ncclAllReduce(dev_words, dev_words, (size_t)count, ncclUint32, ncclMax, comm, ctx->stream));
+    return PBF_OK;
+  }
+  int reduce_status_host(pbf_ctx*, unsigned int*, int) override { return PBF_OK; }
+};
+
+}  // namespace
+
+// Several contexts of ONE process (same or different devices), one host thread per slab inside
+// pbf_group_step.  Messages move with cudaMemcpyPeerAsync on the receiver's stream after waiting
+// for the sender's "packed" event; a host barrier orders the publication of pointers and events.
+struct pbf_group {
+  std::vector<pbf_ctx*> ctxs;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  uint64_t generation = 0;
+  bool failed = false;
+  std::vector<cudaEvent_t> packed;                 // per rank
+  std::vector<float4*> send_ptr[2];                // [side][rank], published per exchange
+  std::vector<std::vector<unsigned int>> words;    // status agreement
+  // global ids for upload / download
+  size_t n_global = 0;
+
+  // returns false if the group was aborted
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (failed) return false;
+    const uint64_t gen = generation;
+    if (++arrived == (int)ctxs.size()) {
+      arrived = 0;
+      ++generation;
+      cv.notify_all();
+      return true;
+    }
+    cv.wait(lk, [&] { return generation != gen || failed; });
+    return !failed;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    failed = true;
+    cv.notify_all();
+  }
+};
+
+namespace {
+
+struct LocalTransport : Transport {
+  pbf_group* group = nullptr;
+  int exchange(pbf_ctx* ctx, float4* const send[2], float4* const recv[2], size_t bytes) override {
+    pbf_group* g = group;
+    const int r = ctx->slab.rank, nr = ctx->slab.nranks;
+    if (nr == 1) return PBF_OK;
+    PBF_CUDA(ctx, cudaEventRecord(g->packed[r], ctx->stream));
+    g->send_ptr[0][r] = send[0];
+    g->send_ptr[1][r] = send[1];
+    if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    for (int side = 0; side < 2; ++side) {
+      const int peer = side == 0 ? r - 1 : r + 1;
+      if (peer < 0 || peer >= nr) continue;
+      PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, g->packed[peer], 0));
+      // the peer's message for me is the one it addressed to its other side
+      PBF_CUDA(ctx, cudaMemcpyPeerAsync(recv[side], ctx->device, g->send_ptr[1 - side][peer], g->ctxs[peer]->device,
+                                        bytes, ctx->stream));
+    }
+    if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    return PBF_OK;
+  }
+  int reduce_status_device(pbf_ctx*, unsigned int*, int) override { return PBF_OK; }
+  int reduce_status_host(pbf_ctx* ctx, unsigned int* host_words, int count) override {
+    pbf_group* g = group;
+    const int r = ctx->slab.rank, nr = ctx->slab.nranks;
+    if (nr == 1) return PBF_OK;
+    g->words[r].assign(host_words, host_words + count);
+    if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    for (int p = 0; p < nr; ++p)
+      for (int k = 0; k < count; ++k) host_words[k] = std::max(host_words[k], g->words[p][k]);
+    if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    return PBF_OK;
+  }
+  void abort() override { group->abort(); }
+};
+
+// ---- buffers -----------------------------------------------------------------------------------
+int ensure_slab_buffers(pbf_ctx* ctx) {
+  SlabState& sl = ctx->slab;
+  if (!sl.counts.p) {
+    PBF_CUDA(ctx, sl.counts.reserve(1));
+    PBF_CUDA(ctx, cudaMemset(sl.counts.p, 0, sizeof(SlabCounts)));
+    PBF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&sl.counts_host), sizeof(SlabCounts)));
+    std::memset(sl.counts_host, 0, sizeof(SlabCounts));
+  }
+  const size_t elems = 1 + 2 * (size_t)std::max(sl.mcap, sl.gcap);
+  if (elems > sl.msg_elems) {
+    for (int p = 0; p < 2; ++p)
+      for (int side = 0; side < 2; ++side) {
+        PBF_CUDA(ctx, sl.send[p][side].reserve(elems));
+        PBF_CUDA(ctx, cudaMemset(sl.send[p][side].p, 0, elems * sizeof(float4)));
+      }
+    for (int side = 0; side < 2; ++side) {
+      PBF_CUDA(ctx, sl.recv[side].reserve(elems));
+      // a missing neighbour never writes its message: the zero header means "0 particles"
+      PBF_CUDA(ctx, cudaMemset(sl.recv[side].p, 0, elems * sizeof(float4)));
+    }
+    sl.msg_elems = elems;
+  }
+  return PBF_OK;
+}
+
+void slab_fill(pbf_ctx* ctx, SlabBuffers& sb) {
+  SlabState& sl = ctx->slab;
+  sb.counts = sl.counts.p;
+  sb.status = ctx->status.p;
+  sb.gid_o = sl.gid_o.p;
+  sb.keep_pos = sl.keep_pos.p;
+  sb.keep_pred = sl.keep_pred.p;
+  sb.blk_cnt = sl.blk_cnt.p;
+  sb.send[0] = sl.send[sl.parity][0].p;
+  sb.send[1] = sl.send[sl.parity][1].p;
+  sb.recv[0] = sl.recv[0].p;
+  sb.recv[1] = sl.recv[1].p;
+  sb.cut_lo = sl.cut_lo;
+  sb.cut_hi = sl.cut_hi;
+  sb.cap = (int)ctx->cap;
+  sb.tot_cap = (int)sl.tot_cap;
+  sb.mcap = sl.mcap;
+  sb.gcap = sl.gcap;
+}
+
+// One exchange with both neighbours; flips the send-buffer parity for the next one.
+int slab_exchange(pbf_ctx* ctx, SlabBuffers& sb, size_t elems) {
+  SlabState& sl = ctx->slab;
+  stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
+  const int rc = sl.transport->exchange(ctx, sb.send, sb.recv, elems * sizeof(float4));
+  stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
+  if (rc != PBF_OK) return rc;
+  sl.exchanges++;
+  sl.bytes_sent += ((sl.rank > 0) + (sl.rank + 1 < sl.nranks)) * elems * sizeof(float4);
+  sl.parity ^= 1;
+  sb.send[0] = sl.send[sl.parity][0].p;
+  sb.send[1] = sl.send[sl.parity][1].p;
+  return PBF_OK;
+}
+
+// ---- one substep of one slab ---------------------------------------------------------------------
+// Same stages as enqueue_substep (pbf_capi.cu) with migration before the grid build, the ghost
+// build after it and one halo refresh per solver iteration.  Returns launches (< 0: error code).
+int slab_substep(pbf_ctx* ctx) {
+  SlabState& sl = ctx->slab;
+  cudaStream_t s = ctx->stream;
+  const StepConsts& c = ctx->consts;
+  const bool strict = ctx->mode == PBF_MODE_STRICT;
+  StageTimer& t = ctx->timer;
+  GridBuffers g{};
+  fill_grid_buffers(ctx, g);
+  SolveBuffers b{};
+  fill_solve_buffers(ctx, b);
+  SlabBuffers sb{};
+  slab_fill(ctx, sb);
+  NeighborList nl{ctx->nbr_idx.p, ctx->nbr_count.p, ctx->K};
+  const NRef n_own = nref((int)ctx->cap, &sl.counts.p->n_own);
+  const NRef n_tot = nref((int)sl.tot_cap, &sl.counts.p->n_tot);
+  int launches = 0, k, rc;
+
+  stage_mark(ctx, PBF_STAGE_PREDICT, 1);
+  k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n_own, true, s);
+  stage_mark(ctx, PBF_STAGE_PREDICT, 0);
+  t.launches[PBF_STAGE_PREDICT] += k; launches += k;
+
+  // migration: particles whose predicted x-cell left the slab move to the neighbour (hops > 1 only
+  // after a batch found a particle more than one slab away)
+  for (int hop = 0; hop < sl.hops; ++hop) {
+    k = launch_slab_split(ctx->pos_o.p, ctx->pred_o.p, sb, c, s);
+    if ((rc = slab_exchange(ctx, sb, 1 + 2 * (size_t)sl.mcap)) != PBF_OK) return rc;
+    k += launch_slab_merge(ctx->pos_o.p, ctx->pred_o.p, sb, c, hop == sl.hops - 1, s);
+    t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
+  }
+  launches += launch_grid_finalize(g, 2, s);
+  t.launches[PBF_STAGE_PREDICT] += 1;
+
+  int out = 0;
+  stage_mark(ctx, PBF_STAGE_SORT, 1);
+  k = launch_sort(ctx->pred_o.p, c, g, n_own, &out, s);
+  stage_mark(ctx, PBF_STAGE_SORT, 0);
+  t.launches[PBF_STAGE_SORT] += k; launches += k;
+  ctx->sorted_buf = out;
+
+  stage_mark(ctx, PBF_STAGE_CELLS, 1);
+  k = launch_cells_reorder(g.keys[out], g.vals[out], ctx->pred_o.p, ctx->pos_o.p, ctx->pred_a.p, ctx->pos_s.p, g, n_own, s);
+  stage_mark(ctx, PBF_STAGE_CELLS, 0);
+  t.launches[PBF_STAGE_CELLS] += k; launches += k;
+
+  // ghost build: two boundary layers per side, appended after the owned slots
+  k = launch_slab_ghost_pack(g.keys[out], ctx->pred_a.p, ctx->pos_s.p, g, sb, s);
+  if ((rc = slab_exchange(ctx, sb, 1 + 2 * (size_t)sl.gcap)) != PBF_OK) return rc;
+  k += launch_slab_ghost_unpack(ctx->pred_a.p, ctx->pos_s.p, g, sb, c, s);
+  t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
+
+  stage_mark(ctx, PBF_STAGE_NEIGHBORS, 1);
+  k = launch_neighbors(ctx->pred_a.p, c, g, nl, n_tot, s);
+  stage_mark(ctx, PBF_STAGE_NEIGHBORS, 0);
+  t.launches[PBF_STAGE_NEIGHBORS] += k; launches += k;
+
+  const int iters = ctx->params.solver_iterations;
+  if (iters <= 0) {
+    launches += launch_commit_only(b, c, n_own, strict, s);
+    t.launches[PBF_STAGE_FINALIZE] += 1;
+    return launches;
+  }
+  const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
+  const bool final_in_delta = !tail_xsph && !tail_vort;
+  int cur = 0;
+  for (int it = 0; it < iters; ++it) {
+    const bool last = it == iters - 1;
+    stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
+    launches += launch_lambda(b, nl, c, cur, n_tot, strict, s);  // owned + first-layer ghosts
+    stage_mark(ctx, PBF_STAGE_LAMBDA, 0);
+    stage_mark(ctx, PBF_STAGE_DELTA, 1);
+    launches += launch_delta(b, nl, c, cur, last, last && final_in_delta, n_own, strict, s);
+    stage_mark(ctx, PBF_STAGE_DELTA, 0);
+    t.launches[PBF_STAGE_LAMBDA] += 1;
+    t.launches[PBF_STAGE_DELTA] += 1;
+    cur ^= 1;
+    if (last && final_in_delta) break;  // nothing reads the ghosts any more
+    k = launch_slab_halo_pack(b.pred[cur], sb, s);
+    if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
+    k += launch_slab_halo_unpack(b.pred[cur], sb, s);
+    t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
+  }
+  if (final_in_delta) return launches;
+
+  float4* pos = b.pred[cur];
+  launches += launch_slab_ghost_vel(pos, b.pos_s, b.rho, b.vel[0], sb, c, strict, s);
+  t.launches[PBF_STAGE_EXCHANGE] += 1;
+  int vcur = 0;
+  if (tail_xsph) {
+    stage_mark(ctx, PBF_STAGE_XSPH, 1);
+    launches += launch_xsph(b, nl, c, pos, !tail_vort, n_own, strict, s);
+    stage_mark(ctx, PBF_STAGE_XSPH, 0);
+    t.launches[PBF_STAGE_XSPH] += 1;
+    vcur = 1;
+    if (tail_vort) {  // omega of the first-layer ghosts needs the post-XSPH velocity of both layers
+      k = launch_slab_halo_pack(b.vel[1], sb, s);
+      if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
+      k += launch_slab_halo_unpack(b.vel[1], sb, s);
+      t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
+    }
+  }
+  if (tail_vort) {
+    stage_mark(ctx, PBF_STAGE_VORT_OMEGA, 1);
+    launches += launch_vort_omega(b, nl, c, pos, vcur, n_tot, strict, s);
+    stage_mark(ctx, PBF_STAGE_VORT_OMEGA, 0);
+    stage_mark(ctx, PBF_STAGE_VORT_APPLY, 1);
+    launches += launch_vort_apply(b, nl, c, pos, vcur, n_own, strict, s);
+    stage_mark(ctx, PBF_STAGE_VORT_APPLY, 0);
+    t.launches[PBF_STAGE_VORT_OMEGA] += 1;
+    t.launches[PBF_STAGE_VORT_APPLY] += 1;
+  }
+  return launches;
+}
+
+int set_device_count(pbf_ctx* ctx, int n_own) {
+  SlabState& sl = ctx->slab;
+  std::memset(sl.counts_host, 0, sizeof(SlabCounts));
+  sl.counts_host->n_own = n_own;
+  sl.counts_host->n_tot = n_own;
+  PBF_CUDA(ctx, cudaMemcpyAsync(sl.counts.p, sl.counts_host, sizeof(SlabCounts), cudaMemcpyHostToDevice, ctx->stream));
+  return PBF_OK;
+}
+
+}  // namespace
+
+namespace pbf {
+
+void slab_release(pbf_ctx* ctx) {
+  SlabState& sl = ctx->slab;
+  if (sl.owns_transport && sl.transport) delete sl.transport;
+  sl.transport = nullptr;
+  sl.counts.release(); sl.gid_o.release(); sl.gid_bak.release(); sl.blk_cnt.release();
+  sl.keep_pos.release(); sl.keep_pred.release();
+  for (int p = 0; p < 2; ++p)
+    for (int side = 0; side < 2; ++side) sl.send[p][side].release();
+  sl.recv[0].release(); sl.recv[1].release();
+  if (sl.counts_host) cudaFreeHost(sl.counts_host);
+  sl.counts_host = nullptr;
+}
+
+// pbf_step of a slab context.  Every rank of the communicator (or every thread of the group)
+// calls it with the same nsteps; the grow-and-replay decision is taken on max-reduced status
+// words, so all ranks replay together.
+int slab_step(pbf_ctx* ctx, int nsteps) {
+  SlabState& sl = ctx->slab;
+  if (!sl.transport) return fail(ctx, PBF_E_COMM, "pbf_step: slab context without a communicator");
+  int rc;
+  const size_t n0 = ctx->n;
+  sl.n_bak = n0;
+  if (n0) {
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_bak.p, ctx->pos_o.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(sl.gid_bak.p, sl.gid_o.p, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  for (int attempt = 0; attempt < 16; ++attempt) {
+    if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;
+    if ((rc = ensure_tables(ctx)) != PBF_OK) return rc;
+    if ((rc = reset_status(ctx)) != PBF_OK) return rc;
+    if ((rc = set_device_count(ctx, (int)n0)) != PBF_OK) return rc;
+    for (int sidx = 0; sidx < nsteps; ++sidx) {
+      const int k = slab_substep(ctx);
+      if (k < 0) {
+        sl.transport->abort();
+        return k;
+      }
+      ctx->launch_count += (uint64_t)k;
+    }
+    PBF_CUDA(ctx, cudaGetLastError());
+    unsigned int* dev_words = &ctx->status.p->max_neighbors;
+    if ((rc = sl.transport->reduce_status_device(ctx, dev_words, kStatusShared)) != PBF_OK) return rc;
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status_host, ctx->status.p, sizeof(StatusBlock), cudaMemcpyDeviceToHost, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(&ctx->last_desc, ctx->desc.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(sl.counts_host, sl.counts.p, sizeof(SlabCounts), cudaMemcpyDeviceToHost, ctx->stream));
+    const cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    if (se != cudaSuccess) {
+      sl.transport->abort();
+      return fail(ctx, PBF_E_CUDA, std::string("slab batch: ") + cudaGetErrorString(se));
+    }
+    if (ctx->profile) timer_resolve(ctx);
+    if ((rc = sl.transport->reduce_status_host(ctx, &ctx->status_host->max_neighbors, kStatusShared)) != PBF_OK) return rc;
+    const StatusBlock st = *ctx->status_host;
+    ctx->last_status = st;
+    const unsigned actionable = st.grid_overflow | st.nbr_overflow | st.mig_overflow | st.ghost_overflow |
+                                st.own_overflow | st.far_migrant;
+    if (!actionable && st.peer_failed)
+      return fail(ctx, PBF_E_COMM, "pbf_step: a neighbouring slab reported a failed batch but no rank knows why");
+    if (!actionable) {
+      ctx->n = (size_t)sl.counts_host->n_own;
+      for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
+      return PBF_OK;
+    }
+    // Grow whatever overflowed (identically on every rank) and replay the batch from the backup.
+    ctx->batches_retried++;
+    if (st.grid_overflow) {
+      const unsigned long long max_cells = ((unsigned long long)st.max_cells_hi << 32) | st.max_cells_lo;
+      if (max_cells > (1ull << 30))
+        return fail(ctx, PBF_E_CAPACITY, "pbf_step: bounding grid of a slab needs more than 2^30 cells (diverged or non-finite positions)");
+      uint32_t cap = ctx->cell_cap;
+      while ((unsigned long long)cap < max_cells + max_cells / 4) cap <<= 1;
+      ctx->cell_cap = cap;
+    }
+    if (st.nbr_overflow) ctx->K = (int)((st.max_neighbors + st.max_neighbors / 4 + 8 + 7u) & ~7u);
+    if (st.mig_overflow) sl.mcap = (int)(st.max_send + st.max_send / 2 + 1024);
+    if (st.ghost_overflow) sl.gcap = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
+    if (st.far_migrant) {
+      if (sl.hops >= std::max(1, sl.nranks - 1))
+        return fail(ctx, PBF_E_COMM, "pbf_step: a particle is outside every reachable slab (non-finite position?)");
+      sl.hops++;
+    }
+    size_t want = ctx->cap;
+    if (st.own_overflow) want = std::max<size_t>(want, (size_t)st.max_own + st.max_own / 4 + 1024);
+    if (st.own_overflow || st.ghost_overflow) {
+      // tot_cap = cap + 2 * gcap must cover max_own (owned + ghosts)
+      ctx->cap = 0;  // force the resize below
+      if ((rc = ensure_particles(ctx, want, n0)) != PBF_OK) return rc;
+    }
+    if (n0) {
+      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+      PBF_CUDA(ctx, cudaMemcpyAsync(sl.gid_o.p, sl.gid_bak.p, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  return fail(ctx, PBF_E_CAPACITY, "pbf_step: slab tables kept overflowing after 16 growth attempts");
+}
+
+}  // namespace pbf
+
+namespace {
+
+// Keeps the particles of this rank's slab out of a global set, in ascending global id.
+int slab_take(pbf_ctx* ctx, size_t n_global, const float* px, const float* py, const float* pz, const float* vx,
+              const float* vy, const float* vz, const std::vector<int>& cuts) {
+  SlabState& sl = ctx->slab;
+  if (n_global > 0xfffffff0ull) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload: more than 2^32 particles");
+  if (!(ctx->params.h > 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload: set the parameters first (h is needed for the cuts)");
+  cudaSetDevice(ctx->device);
+  sl.cut_lo = cuts[(size_t)sl.rank];
+  sl.cut_hi = cuts[(size_t)sl.rank + 1];
+  const float inv_h = 1.0f / ctx->params.h;
+  std::vector<uint32_t> gid;
+  std::vector<float4> pos, vel;
+  for (size_t i = 0; i < n_global; ++i) {
+    const int c = host_cell(px[i], inv_h);
+    if (c < sl.cut_lo || c >= sl.cut_hi) continue;
+    gid.push_back((uint32_t)i);
+    pos.push_back(make_float4(px[i], py[i], pz[i], 0.0f));
+    vel.push_back(make_float4(vx[i], vy[i], vz[i], 0.0f));
+  }
+  const size_t n = gid.size();
+  const size_t cap = n + n / 4 + 4096;
+  if (sl.gcap == 0) sl.gcap = (int)std::max<size_t>(16384, cap / 2);
+  if (sl.mcap == 0) sl.mcap = (int)std::max<size_t>(8192, cap / 16);
+  int rc = ensure_particles(ctx, cap, 0);
+  if (rc != PBF_OK) return rc;
+  if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;
+  if (n) {
+    PBF_CUDA(ctx, cudaMemcpy(ctx->pos_o.p, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    PBF_CUDA(ctx, cudaMemcpy(ctx->vel_o.p, vel.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    PBF_CUDA(ctx, cudaMemcpy(sl.gid_o.p, gid.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  ctx->n = n;
+  return PBF_OK;
+}
+
+int slab_enable(pbf_ctx* ctx, int rank, int nranks, Transport* tr, bool owns) {
+  SlabState& sl = ctx->slab;
+  if (sl.transport && sl.owns_transport) delete sl.transport;
+  sl.enabled = true;
+  sl.rank = rank;
+  sl.nranks = nranks;
+  sl.transport = tr;
+  sl.owns_transport = owns;
+  sl.hops = 1;
+  invalidate_graph(ctx);
+  ctx->cap = 0;  // the per-particle buffers are re-sized for the slab layout on the next upload
+  return PBF_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
 extern "C" {
 
+int pbf_slab_plan(size_t n, const float* px, float h, int nranks, int32_t* cuts) {
+  if (!cuts || nranks < 1 || !(h > 0.0f) || (n > 0 && !px)) return fail(nullptr, PBF_E_INVALID, "pbf_slab_plan: bad arguments");
+  std::vector<int> c;
+  std::string err;
+  const int rc = plan_cuts(n, px, h, nranks, c, err);
+  if (rc != PBF_OK) return fail(nullptr, rc, err);
+  for (int r = 0; r <= nranks; ++r) cuts[r] = c[(size_t)r];
+  return PBF_OK;
+}
+
 int pbf_comm_unique_id(void* id_bytes) {
-  if (id_bytes) std::memset(id_bytes, 0, PBF_COMM_ID_BYTES);
-  return PBF_E_COMM;
+  if (!id_bytes) return PBF_E_INVALID;
+  static_assert(sizeof(ncclUniqueId) <= PBF_COMM_ID_BYTES, "ncclUniqueId does not fit PBF_COMM_ID_BYTES");
+  ncclUniqueId id;
+  const ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, PBF_E_COMM, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+  std::memset(id_bytes, 0, PBF_COMM_ID_BYTES);
+  std::memcpy(id_bytes, &id, sizeof(id));
+  return PBF_OK;
 }
 
-int pbf_comm_init(pbf_ctx* ctx, int, int, const void*) {
-  if (ctx) ctx->error = "pbf_comm_init: slab exchange is not built yet";
-  return PBF_E_COMM;
+int pbf_comm_init(pbf_ctx* ctx, int rank, int nranks, const void* id_bytes) {
+  if (!ctx || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, PBF_E_INVALID, "pbf_comm_init: bad arguments");
+  cudaSetDevice(ctx->device);
+  NcclTransport* tr = new NcclTransport();
+  tr->rank = rank;
+  tr->nranks = nranks;
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  const ncclResult_t r = ncclCommInitRank(&tr->comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    tr->comm = nullptr;
+    delete tr;
+    return fail(ctx, PBF_E_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+  }
+  return slab_enable(ctx, rank, nranks, tr, true);
 }
 
-int pbf_slab_upload(pbf_ctx* ctx, size_t, const float*, const float*, const float*, const float*,
-                    const float*, const float*) {
-  if (ctx) ctx->error = "pbf_slab_upload: slab exchange is not built yet";
-  return PBF_E_COMM;
+int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float* py, const float* pz,
+                    const float* vx, const float* vy, const float* vz) {
+  if (!ctx || !ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload: call pbf_comm_init (or pbf_group_create) first");
+  if (n_global > 0 && (!px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload: null array");
+  std::vector<int> cuts;
+  std::string err;
+  const int rc = plan_cuts(n_global, px, ctx->params.h, ctx->slab.nranks, cuts, err);
+  if (rc != PBF_OK) return fail(ctx, rc, err);
+  return slab_take(ctx, n_global, px, py, pz, vx, vy, vz, cuts);
+}
+
+// The per-rank analogue of pbf_upload: this rank's own particles (ascending global id, all inside
+// its cuts) from host arrays; the cuts of the last pbf_slab_upload are kept.
+int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, const float* px, const float* py,
+                          const float* pz, const float* vx, const float* vy, const float* vz) {
+  if (!ctx || !ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: not a slab context");
+  if (n > 0 && (!global_id || !px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: null array");
+  cudaSetDevice(ctx->device);
+  int rc = ensure_particles(ctx, std::max(n, ctx->cap), ctx->n);
+  if (rc != PBF_OK) return rc;
+  const float inv_h = 1.0f / ctx->params.h;
+  std::vector<uint32_t> gid(n);
+  std::vector<float4> pos(n), vel(n);
+  for (size_t i = 0; i < n; ++i) {
+    if (global_id[i] < 0 || global_id[i] > 0xfffffff0ll || (i > 0 && global_id[i] <= global_id[i - 1]))
+      return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: global ids must be ascending and unique");
+    const int c = host_cell(px[i], inv_h);
+    if (c < ctx->slab.cut_lo || c >= ctx->slab.cut_hi)
+      return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: a particle lies outside this slab's cuts");
+    gid[i] = (uint32_t)global_id[i];
+    pos[i] = make_float4(px[i], py[i], pz[i], 0.0f);
+    vel[i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
+  }
+  if (n) {
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, vel.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->slab.gid_o.p, gid.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->n = n;
+  return PBF_OK;
 }
 
 size_t pbf_slab_owned(const pbf_ctx* ctx) { return ctx ? ctx->n : 0; }
 
-int pbf_slab_download(pbf_ctx* ctx, int64_t*, float*, float*, float*, float*, float*, float*) {
-  if (ctx) ctx->error = "pbf_slab_download: slab exchange is not built yet";
-  return PBF_E_COMM;
+int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi) {
+  if (!ctx || !ctx->slab.enabled) return PBF_E_INVALID;
+  if (lo) *lo = ctx->slab.cut_lo;
+  if (hi) *hi = ctx->slab.cut_hi;
+  return PBF_OK;
+}
+
+int pbf_slab_stats(const pbf_ctx* ctx, uint64_t* exchanges, uint64_t* bytes_sent, int32_t* ghosts, int32_t* hops) {
+  if (!ctx || !ctx->slab.enabled) return PBF_E_INVALID;
+  if (exchanges) *exchanges = ctx->slab.exchanges;
+  if (bytes_sent) *bytes_sent = ctx->slab.bytes_sent;
+  if (ghosts) *ghosts = ctx->slab.counts_host ? ctx->slab.counts_host->n_ghost[0] + ctx->slab.counts_host->n_ghost[1] : 0;
+  if (hops) *hops = ctx->slab.hops;
+  return PBF_OK;
+}
+
+int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py, float* pz, float* vx, float* vy,
+                      float* vz) {
+  if (!ctx || !ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_slab_download: not a slab context");
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->n;
+  if (n == 0) return PBF_OK;
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<float4> pos(n), vel(n);
+  std::vector<uint32_t> gid(n);
+  PBF_CUDA(ctx, cudaMemcpy(pos.data(), ctx->pos_o.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  PBF_CUDA(ctx, cudaMemcpy(vel.data(), ctx->vel_o.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  PBF_CUDA(ctx, cudaMemcpy(gid.data(), ctx->slab.gid_o.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    if (global_id) global_id[i] = (int64_t)gid[i];
+    if (px) px[i] = pos[i].x;
+    if (py) py[i] = pos[i].y;
+    if (pz) pz[i] = pos[i].z;
+    if (vx) vx[i] = vel[i].x;
+    if (vy) vy[i] = vel[i].y;
+    if (vz) vz[i] = vel[i].z;
+  }
+  return PBF_OK;
+}
+
+// ---- in-process group (several slabs driven by one process) ------------------------------------
+pbf_group* pbf_group_create(pbf_ctx** ctxs, int n) {
+  if (!ctxs || n < 1) {
+    fail(nullptr, PBF_E_INVALID, "pbf_group_create: bad arguments");
+    return nullptr;
+  }
+  pbf_group* g = new pbf_group();
+  g->ctxs.assign(ctxs, ctxs + n);
+  g->packed.resize((size_t)n);
+  g->send_ptr[0].assign((size_t)n, nullptr);
+  g->send_ptr[1].assign((size_t)n, nullptr);
+  g->words.resize((size_t)n);
+  for (int r = 0; r < n; ++r) {
+    cudaSetDevice(ctxs[r]->device);
+    cudaEventCreateWithFlags(&g->packed[(size_t)r], cudaEventDisableTiming);
+    for (int p = 0; p < n; ++p) {  // peer access between distinct devices (ignored when already on / unsupported)
+      if (ctxs[p]->device != ctxs[r]->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[p]->device);
+        if (can && cudaDeviceEnablePeerAccess(ctxs[p]->device, 0) != cudaSuccess) cudaGetLastError();
+      }
+    }
+    LocalTransport* tr = new LocalTransport();
+    tr->group = g;
+    slab_enable(ctxs[r], r, n, tr, true);
+  }
+  return g;
+}
+
+void pbf_group_destroy(pbf_group* g) {
+  if (!g) return;
+  for (size_t r = 0; r < g->ctxs.size(); ++r) {
+    cudaSetDevice(g->ctxs[r]->device);
+    cudaStreamSynchronize(g->ctxs[r]->stream);
+    cudaEventDestroy(g->packed[r]);
+    SlabState& sl = g->ctxs[r]->slab;
+    if (sl.owns_transport && sl.transport) delete sl.transport;
+    sl.transport = nullptr;
+    sl.enabled = false;
+  }
+  delete g;
+}
+
+int pbf_group_upload(pbf_group* g, size_t n_global, const float* px, const float* py, const float* pz,
+                     const float* vx, const float* vy, const float* vz) {
+  if (!g) return PBF_E_INVALID;
+  g->n_global = n_global;
+  for (pbf_ctx* ctx : g->ctxs) {
+    const int rc = pbf_slab_upload(ctx, n_global, px, py, pz, vx, vy, vz);
+    if (rc != PBF_OK) return rc;
+  }
+  return PBF_OK;
+}
+
+int pbf_group_step(pbf_group* g, int nsteps) {
+  if (!g || nsteps < 0) return PBF_E_INVALID;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->failed = false;
+    g->arrived = 0;
+  }
+  const size_t n = g->ctxs.size();
+  std::vector<int> rcs(n, PBF_OK);
+  std::vector<std::thread> threads;
+  for (size_t r = 0; r < n; ++r)
+    threads.emplace_back([g, r, nsteps, &rcs] {
+      rcs[r] = pbf_step(g->ctxs[r], nsteps);
+      if (rcs[r] != PBF_OK) g->abort();
+    });
+  for (auto& th : threads) th.join();
+  for (size_t r = 0; r < n; ++r)
+    if (rcs[r] != PBF_OK) return rcs[r];
+  return PBF_OK;
+}
+
+// Gathers every slab into global arrays in ORIGINAL particle order (State order).
+int pbf_group_download(pbf_group* g, float* px, float* py, float* pz, float* vx, float* vy, float* vz) {
+  if (!g) return PBF_E_INVALID;
+  size_t seen = 0;
+  for (pbf_ctx* ctx : g->ctxs) {
+    const size_t n = ctx->n;
+    std::vector<int64_t> gid(n);
+    std::vector<float> a[6];
+    for (auto& v : a) v.resize(n);
+    const int rc = pbf_slab_download(ctx, gid.data(), a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data());
+    if (rc != PBF_OK) return rc;
+    float* dst[6] = {px, py, pz, vx, vy, vz};
+    for (size_t i = 0; i < n; ++i) {
+      if ((size_t)gid[i] >= g->n_global) return fail(ctx, PBF_E_INVALID, "pbf_group_download: global id out of range");
+      for (int k = 0; k < 6; ++k)
+        if (dst[k]) dst[k][gid[i]] = a[k][i];
+    }
+    seen += n;
+  }
+  if (seen != g->n_global) return fail(g->ctxs[0], PBF_E_COMM, "pbf_group_download: slabs do not add up to the global particle count");
+  return PBF_OK;
+}
+
+size_t pbf_group_count(const pbf_group* g) { return g ? g->n_global : 0; }
+
+// Test hook (not in pbf_b200.h): shrink the message capacities so that the overflow -> grow ->
+// replay path of a slab batch can be exercised on small inputs.  Call before pbf_slab_upload.
+int pbf_debug_set_slab_capacity(pbf_ctx* ctx, int mcap, int gcap) {
+  if (!ctx || mcap < 1 || gcap < 1) return PBF_E_INVALID;
+  ctx->slab.mcap = mcap;
+  ctx->slab.gcap = gcap;
+  return PBF_OK;
 }
 
 }  // extern "C"

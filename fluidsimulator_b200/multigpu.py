@@ -1,0 +1,236 @@
+"""Multi-process driver of the x-slab decomposition: one rank per GPU (torchrun), NCCL send/recv
+between x-neighbours inside libpbf_b200.so.  torch.distributed is plumbing only:
+it ships the NCCL unique id, gathers results for checks and takes the max over ranks of the
+device-timed region.
+
+  torchrun --nproc-per-node N -m fluidsimulator_b200.multigpu --check --scene fluid_large --steps 10
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import time
+
+import numpy as np
+
+from .capi import PBF_MODE_FAST, PBF_MODE_STRICT, SlabSolver, Solver, comm_unique_id, slab_plan
+
+
+# ---- host-side logic (also exercised on CPU with the gloo backend, tests/test_multigpu_host.py) ---
+def cell_x(px: np.ndarray, h: float) -> np.ndarray:
+    """x-cell of a position: floor(x * (1.0f / h)) in float32 (reference core.cpp:28-34)."""
+    inv = np.float32(1.0) / np.float32(h)
+    return np.floor(px.astype(np.float32) * inv).astype(np.int64)
+
+
+def owned_mask(px: np.ndarray, h: float, cuts: np.ndarray, rank: int) -> np.ndarray:
+    c = cell_x(px, h)
+    return (c >= int(cuts[rank])) & (c < int(cuts[rank + 1]))
+
+
+def broadcast_bytes(dist, payload: bytes | None, nbytes: int, device) -> bytes:
+    """Rank 0's `payload` to every rank (uint8 tensor on `device`: works for nccl and gloo)."""
+    import torch
+    t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if dist.get_rank() == 0:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def gather_global(dist, gid: np.ndarray, state6, n_global: int, device):
+    """Every rank's (global ids, SoA state) assembled on rank 0 in original particle order.
+    Returns the six global arrays on rank 0, None elsewhere."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = gid.shape[0]
+    dist.all_reduce(counts)
+    nmax = int(counts.max().item())
+    mine = torch.zeros((7, nmax), dtype=torch.float64, device=device)  # float64 holds ids < 2^53 and float32 exactly
+    mine[0, : gid.shape[0]] = torch.from_numpy(gid.astype(np.float64)).to(device)
+    for k in range(6):
+        mine[1 + k, : gid.shape[0]] = torch.from_numpy(state6[k].astype(np.float64)).to(device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    if rank != 0:
+        return None
+    out = [np.full(n_global, np.nan, dtype=np.float32) for _ in range(6)]
+    seen = 0
+    for r in range(world):
+        n = int(counts[r].item())
+        block = parts[r].cpu().numpy()
+        ids = block[0, :n].astype(np.int64)
+        for k in range(6):
+            out[k][ids] = block[1 + k, :n].astype(np.float32)
+        seen += n
+    if seen != n_global:
+        raise RuntimeError(f"slabs hold {seen} particles, expected {n_global}")
+    return out
+
+
+# ---- GPU side ------------------------------------------------------------------------------------
+def make_slab(dist, local: int, params, planes, state, mode, stream_ptr=None) -> SlabSolver:
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = torch.device("cuda", local)
+    uid = broadcast_bytes(dist, comm_unique_id() if rank == 0 else None, 128, device)
+    sol = SlabSolver(local, 0, mode)
+    sol.set_params(params)
+    sol.set_planes(planes)
+    if stream_ptr is not None:
+        sol.set_stream(stream_ptr)
+    sol.comm_init(rank, world, uid)
+    sol.slab_upload(state)
+    return sol
+
+
+def bench(args, flags, rank: int, world: int, local: int):
+    """bench.py's N > 1 arm: strong scaling of one scene over `world` slabs (or --weak)."""
+    import torch
+    import torch.distributed as dist
+    import bench as B
+
+    scene = args.scene if not args.weak else f"weak_{world}"
+    params, planes, state = B.load_scene(scene, flags, args.iterations)
+    n = len(state[0])
+    mode = PBF_MODE_STRICT if args.mode == "strict" else PBF_MODE_FAST
+    device = torch.device("cuda", local)
+    stream = torch.cuda.Stream()
+    sol = make_slab(dist, local, params, planes, state, mode, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        if args.presteps:
+            sol.step(args.presteps)
+        sol.step(args.warmup)
+        barrier()
+        sampler = B.ClockSampler(local)
+        launches0 = sol.launch_count()
+        stats0 = sol.slab_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        ev0.record(stream)
+        sol.step(args.steps)
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms_t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        ms = float(ms_t.item())
+        launches = sol.launch_count() - launches0
+        stats1 = sol.slab_stats()
+        owned = sol.owned()
+
+        # per-stage split of this rank (profiling mode: CUDA events around every stage)
+        sol.profile_enable(True)
+        sol.profile_reset()
+        sol.step(min(args.steps, 20))
+        torch.cuda.synchronize()
+        prof = sol.profile()
+        sol.profile_enable(False)
+        psteps = min(args.steps, 20)
+
+        # e2e: every rank round-trips ITS particles through pinned host memory each substep
+        gid, st = sol.slab_download()
+        host = [torch.from_numpy(a).pin_memory().numpy() for a in st]
+        e2e_steps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        moved = 0
+        for _ in range(e2e_steps):
+            sol.slab_upload_owned(gid, host)
+            sol.step(1)
+            gid, st = sol.slab_download()
+            moved += 2 * 24 * gid.shape[0]
+            host = st
+        barrier()
+        e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+
+    tot_launch = torch.tensor([launches], dtype=torch.int64, device=device)
+    dist.all_reduce(tot_launch)
+    owned_t = torch.zeros(world, dtype=torch.int64, device=device)
+    owned_t[rank] = owned
+    dist.all_reduce(owned_t)
+    if rank != 0:
+        return
+    value = n * args.steps / (ms * 1e-3)
+    peak, peak_src = B.measured_peaks()
+    stages = {k: {"ms_per_step": v["ms"] / psteps, "launches_per_step": v["launches"] / psteps}
+              for k, v in prof.items() if v["launches"]}
+    solver = {k: v for k, v in stages.items() if k in ("lambda", "delta")}
+    dom = max(solver, key=lambda k: solver[k]["ms_per_step"]) if solver else None
+    roofline = None
+    if dom:
+        per_launch_s = 1e-3 * prof[dom]["ms"] / prof[dom]["launches"]
+        achieved = B.ALG_BYTES[dom] * owned / per_launch_s / 1e9   # rank 0's slab, rank 0's kernel
+        roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "scope": "rank 0, per GPU",
+                    "alg_bytes_per_particle": B.ALG_BYTES[dom], "avg_launch_ms": per_launch_s * 1e3,
+                    "whole_step_frac": B.b_alg(args.iterations, flags) * value / 1e9 / (peak * world)}
+    line = {
+        "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": scene, "particles": n, "solver_iterations": args.iterations, "flags": args.flags,
+                   "mode": args.mode, "dt": "1/120", "presteps": args.presteps,
+                   "decomposition": f"{world} x-slabs, 2 ghost layers, NCCL send/recv between x-neighbours",
+                   "owned_per_rank": [int(x) for x in owned_t.tolist()],
+                   "l2": "per-slab working set (neighbour list + particle arrays) re-streamed every substep; no explicit flush"},
+        "roofline": roofline, "cpu_baseline": None,
+        "e2e": {"value": n * e2e_steps / float(e2e_t.item()), "unit": "particle-substeps/s",
+                "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
+                "call": "per rank: pbf_slab_upload_owned + pbf_step(1) + pbf_slab_download"},
+        "gpu_launches": int(tot_launch.item()), "clocks": clocks, "stages": stages,
+        "exchange": {"per_substep": (stats1["exchanges"] - stats0["exchanges"]) / args.steps,
+                     "bytes_per_substep_rank0": (stats1["bytes_sent"] - stats0["bytes_sent"]) / args.steps,
+                     "ghosts_rank0": stats1["ghosts"], "hops": stats1["hops"]},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import bench as B
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true", help="compare the slab result with one GPU, bit for bit")
+    ap.add_argument("--scene", default="fluid_large")
+    ap.add_argument("--flags", default="all")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--iterations", type=int, default=4)
+    args = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank()
+    params, planes, state = B.load_scene(args.scene, B.FLAGSETS[args.flags], args.iterations)
+    sol = make_slab(dist, local, params, planes, state, PBF_MODE_STRICT)
+    sol.step(args.steps)
+    gid, st = sol.slab_download()
+    full = gather_global(dist, gid, st, len(state[0]), torch.device("cuda", local))
+    ok = True
+    if rank == 0:
+        ref = Solver(local, len(state[0]), PBF_MODE_STRICT)
+        ref.set_params(params)
+        ref.set_planes(planes)
+        ref.upload(state)
+        ref.step(args.steps)
+        bad = [k for k, (a, b) in enumerate(zip(full, ref.download()))
+               if not np.array_equal(a.view(np.uint32), b.view(np.uint32))]
+        ok = not bad
+        print(f"slab check {'ok' if ok else 'FAILED ' + str(bad)}: {args.scene}, {dist.get_world_size()} slabs, "
+              f"{args.steps} substeps, stats {sol.slab_stats()}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    raise SystemExit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -185,24 +185,57 @@ int pbf_profile_get(pbf_ctx* ctx, int stage, double* total_ms, uint64_t* launche
  * by the kernels they contain). */
 uint64_t pbf_launch_count(const pbf_ctx* ctx);
 
-/* ---- slab decomposition (one ctx per rank; x-slabs) ------------ */
+/* ---- slab decomposition (one ctx per GPU; x-slabs) ----
+ * The reference has no multi-GPU path.  Large scenes are split into slabs of x-cells; every
+ * substep exchanges migrating particles and two ghost layers with the x-neighbours and refreshes
+ * the ghosts once per solver iteration.  STRICT results are bit-identical to a single GPU. */
 
-/* Size in bytes of the opaque id produced by pbf_comm_unique_id. */
+/* Host-only planning: cuts[0..nranks] on x-cell boundaries (cuts[0] = INT32_MIN, cuts[nranks] =
+ * INT32_MAX) with nearly equal particle counts and >= 2 cell layers per slab; slab r owns the
+ * x-cells [cuts[r], cuts[r+1]).  Cell of a position: floor(x * (1.0f / h)) (core.cpp:28-34). */
+int pbf_slab_plan(size_t n, const float* px, float h, int nranks, int32_t* cuts);
+
+/* Multi-process transport (NCCL send/recv between x-neighbours). */
 #define PBF_COMM_ID_BYTES 128
 /* Rank 0 calls this and ships the bytes to every rank by any host channel
  * (torch.distributed broadcast, a file, MPI...). */
 int pbf_comm_unique_id(void* id_bytes);
-/* Joins the NCCL communicator of `nranks` slabs.  Collective. */
+/* Joins the NCCL communicator of `nranks` slabs and turns ctx into slab `rank`.  Collective. */
 int pbf_comm_init(pbf_ctx* ctx, int rank, int nranks, const void* id_bytes);
-/* Distributes a global particle set: every rank passes the SAME global arrays and
- * keeps the particles of its x-slab (cuts on cell boundaries, equal counts).
- * Global original ids are retained for gathering. */
+
+/* Distributes a global particle set: every rank passes the SAME global arrays (after
+ * pbf_set_params) and keeps the particles of its slab; global ids = indices into these arrays. */
 int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float* py,
                     const float* pz, const float* vx, const float* vy, const float* vz);
-/* Number of particles currently owned by this slab, and their global ids. */
+/* This rank's own particles only (ascending global ids, inside its cuts): the per-rank analogue
+ * of pbf_upload.  The cuts of the last pbf_slab_upload stay. */
+int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, const float* px,
+                          const float* py, const float* pz, const float* vx, const float* vy,
+                          const float* vz);
+/* Particles currently owned by this slab (changes as particles migrate), its cuts, and the
+ * owned particles with their global ids (ascending). */
 size_t pbf_slab_owned(const pbf_ctx* ctx);
+int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi);
 int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py,
                       float* pz, float* vx, float* vy, float* vz);
+/* Exchanges and bytes sent since creation, ghosts held after the last substep, migration hops. */
+int pbf_slab_stats(const pbf_ctx* ctx, uint64_t* exchanges, uint64_t* bytes_sent,
+                   int32_t* ghosts, int32_t* hops);
+/* pbf_step on a slab context is collective: every rank calls it with the same nsteps. */
+
+/* Single-process transport: `n` contexts (on the same or on different devices) become slabs
+ * 0..n-1 linked by peer copies; pbf_group_step runs one host thread per slab.  Destroy the
+ * group before its contexts. */
+typedef struct pbf_group pbf_group;
+pbf_group* pbf_group_create(pbf_ctx** ctxs, int n);
+void pbf_group_destroy(pbf_group* group);
+int pbf_group_upload(pbf_group* group, size_t n_global, const float* px, const float* py,
+                     const float* pz, const float* vx, const float* vy, const float* vz);
+int pbf_group_step(pbf_group* group, int nsteps);
+/* All slabs gathered into global arrays in original particle order (any pointer may be NULL). */
+int pbf_group_download(pbf_group* group, float* px, float* py, float* pz, float* vx,
+                       float* vy, float* vz);
+size_t pbf_group_count(const pbf_group* group);
 
 #ifdef __cplusplus
 }
