@@ -382,12 +382,17 @@ class SlabSolver(Solver):
         self._check(self.lib.pbf_slab_cuts(self.ctx, iptr(lo), iptr(hi)))
         return int(lo[0]), int(hi[0])
 
-    def slab_download(self):
+    def slab_download(self, out=None):
+        """(global ids, six SoA arrays) of the owned particles.  `out` = (int64 array, six float32
+        arrays) of sufficient capacity (e.g. pinned) to receive them in place."""
         n = self.owned()
-        gid = np.empty(n, dtype=np.int64)
-        out = [np.empty(n, dtype=np.float32) for _ in range(6)]
-        self._check(self.lib.pbf_slab_download(self.ctx, gid.ctypes.data_as(_i64p), *[fptr(a) for a in out]))
-        return gid, out
+        if out is None:
+            gid = np.empty(n, dtype=np.int64)
+            arrs = [np.empty(n, dtype=np.float32) for _ in range(6)]
+        else:
+            gid, arrs = out[0][:n], [a[:n] for a in out[1]]
+        self._check(self.lib.pbf_slab_download(self.ctx, gid.ctypes.data_as(_i64p), *[fptr(a) for a in arrs]))
+        return gid, arrs
 
     def slab_stats(self) -> dict:
         ex, by = C.c_uint64(0), C.c_uint64(0)

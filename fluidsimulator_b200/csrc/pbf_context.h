@@ -58,6 +58,8 @@ struct Transport {
   // ... or of its host copy after the batch's synchronisation (whichever the transport supports)
   virtual int reduce_status_host(pbf_ctx* ctx, unsigned int* host_words, int count) = 0;
   virtual void abort() {}
+  // true when exchange() is purely stream-ordered, i.e. may be recorded into a CUDA graph
+  virtual bool capturable() const { return false; }
 };
 
 struct SlabState {
@@ -72,6 +74,9 @@ struct SlabState {
   size_t n_bak = 0;                        // owned count at the start of the batch
   uint64_t exchanges = 0;
   uint64_t bytes_sent = 0;
+  uint64_t graph_exchanges = 0, graph_bytes = 0;  // per replay of the captured substep
+  bool warm = false;                       // a batch has completed since the communicator was joined
+  bool fixed_caps = false;                 // keep the message capacities (no adaptive shrinking)
   Transport* transport = nullptr;          // not owned when it belongs to a group
   bool owns_transport = false;
   DevBuf<SlabCounts> counts;
@@ -79,6 +84,7 @@ struct SlabState {
   DevBuf<float4> keep_pos, keep_pred;
   DevBuf<float4> send[2][2], recv[2];      // [parity][side], [side]
   SlabCounts* counts_host = nullptr;       // pinned
+  std::vector<uint32_t> gid_host;          // staging of global ids for upload / download
 };
 
 struct StageTimer {

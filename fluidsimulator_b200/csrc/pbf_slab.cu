@@ -108,6 +108,7 @@ struct NcclTransport : Transport {
     return PBF_OK;
   }
   int reduce_status_host(pbf_ctx*, unsigned int*, int) override { return PBF_OK; }
+  bool capturable() const override { return true; }  // ncclSend/ncclRecv record into a CUDA graph
 };
 
 }  // namespace
@@ -267,6 +268,9 @@ int slab_substep(pbf_ctx* ctx) {
   const NRef n_own = nref((int)ctx->cap, &sl.counts.p->n_own);
   const NRef n_tot = nref((int)sl.tot_cap, &sl.counts.p->n_tot);
   int launches = 0, k, rc;
+  // A replayed graph bakes the send-buffer pointers in: every substep must start on the same pair.
+  // (Stream-ordered transports have no write-after-read hazard on the send buffers.)
+  if (sl.transport->capturable()) sl.parity = 0;
 
   stage_mark(ctx, PBF_STAGE_PREDICT, 1);
   k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n_own, true, s);
@@ -410,13 +414,43 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     if ((rc = ensure_tables(ctx)) != PBF_OK) return rc;
     if ((rc = reset_status(ctx)) != PBF_OK) return rc;
     if ((rc = set_device_count(ctx, (int)n0)) != PBF_OK) return rc;
+    // Stream-ordered transports (NCCL) let the whole substep, exchanges included, replay as one
+    // CUDA graph.  The first batch after joining the communicator runs un-captured so that NCCL
+    // can set up its peer connections outside a capture.
+    const bool graph = ctx->use_graph && !ctx->profile && sl.transport->capturable() && sl.warm;
     for (int sidx = 0; sidx < nsteps; ++sidx) {
-      const int k = slab_substep(ctx);
-      if (k < 0) {
-        sl.transport->abort();
-        return k;
+      if (graph) {
+        if (!ctx->graph_exec) {
+          cudaGraph_t gr = nullptr;
+          const uint64_t ex0 = sl.exchanges, by0 = sl.bytes_sent;
+          uint64_t saved[PBF_STAGE_COUNT];
+          std::memcpy(saved, ctx->timer.launches, sizeof(saved));
+          PBF_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+          const int k = slab_substep(ctx);
+          const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &gr);
+          std::memcpy(ctx->timer.launches, saved, sizeof(saved));
+          if (k < 0) return k;
+          PBF_CUDA(ctx, ce);
+          ctx->graph_kernels = k;
+          sl.graph_exchanges = sl.exchanges - ex0;
+          sl.graph_bytes = sl.bytes_sent - by0;
+          sl.exchanges = ex0;
+          sl.bytes_sent = by0;
+          PBF_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, gr, 0));
+          cudaGraphDestroy(gr);
+        }
+        PBF_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        ctx->launch_count += (uint64_t)ctx->graph_kernels;
+        sl.exchanges += sl.graph_exchanges;
+        sl.bytes_sent += sl.graph_bytes;
+      } else {
+        const int k = slab_substep(ctx);
+        if (k < 0) {
+          sl.transport->abort();
+          return k;
+        }
+        ctx->launch_count += (uint64_t)k;
       }
-      ctx->launch_count += (uint64_t)k;
     }
     PBF_CUDA(ctx, cudaGetLastError());
     unsigned int* dev_words = &ctx->status.p->max_neighbors;
@@ -440,8 +474,23 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     if (!actionable) {
       ctx->n = (size_t)sl.counts_host->n_own;
       for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
+      sl.warm = true;
+      // Messages are sent at full capacity (their size is not known to the host), so capacities
+      // follow the observed maxima down as well as up.  The maxima are max-reduced over the slabs:
+      // every rank takes the same decision.
+      if (!sl.fixed_caps) {
+        const int want_g = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
+        const int want_m = (int)(st.max_send + st.max_send / 2 + 1024);
+        if (want_g < sl.gcap - sl.gcap / 4 || want_m < sl.mcap / 2) {
+          if (want_g < sl.gcap - sl.gcap / 4) sl.gcap = want_g;
+          if (want_m < sl.mcap / 2) sl.mcap = want_m;
+          sl.tot_cap = ctx->cap + 2 * (size_t)sl.gcap;
+          invalidate_graph(ctx);
+        }
+      }
       return PBF_OK;
     }
+    invalidate_graph(ctx);
     // Grow whatever overflowed (identically on every rank) and replay the batch from the backup.
     ctx->batches_retried++;
     if (st.grid_overflow) {
@@ -492,15 +541,22 @@ int slab_take(pbf_ctx* ctx, size_t n_global, const float* px, const float* py, c
   const float inv_h = 1.0f / ctx->params.h;
   std::vector<uint32_t> gid;
   std::vector<float4> pos, vel;
+  std::vector<size_t> per_rank((size_t)sl.nranks, 0);
   for (size_t i = 0; i < n_global; ++i) {
     const int c = host_cell(px[i], inv_h);
+    size_t r = 0;
+    while (r + 1 < (size_t)sl.nranks && c >= cuts[r + 1]) ++r;
+    per_rank[r]++;
     if (c < sl.cut_lo || c >= sl.cut_hi) continue;
     gid.push_back((uint32_t)i);
     pos.push_back(make_float4(px[i], py[i], pz[i], 0.0f));
     vel.push_back(make_float4(vx[i], vy[i], vz[i], 0.0f));
   }
   const size_t n = gid.size();
-  const size_t cap = n + n / 4 + 4096;
+  // Message capacities are part of the wire format (fixed-size messages, payload offsets), so
+  // they are derived from the LARGEST slab: every rank computes the same numbers.
+  const size_t n_max = *std::max_element(per_rank.begin(), per_rank.end());
+  const size_t cap = n_max + n_max / 4 + 4096;
   if (sl.gcap == 0) sl.gcap = (int)std::max<size_t>(16384, cap / 2);
   if (sl.mcap == 0) sl.mcap = (int)std::max<size_t>(8192, cap / 16);
   int rc = ensure_particles(ctx, cap, 0);
@@ -592,23 +648,21 @@ int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, cons
   cudaSetDevice(ctx->device);
   int rc = ensure_particles(ctx, std::max(n, ctx->cap), ctx->n);
   if (rc != PBF_OK) return rc;
-  const float inv_h = 1.0f / ctx->params.h;
-  std::vector<uint32_t> gid(n);
-  std::vector<float4> pos(n), vel(n);
+  std::vector<uint32_t>& gid = ctx->slab.gid_host;
+  gid.resize(n);
   for (size_t i = 0; i < n; ++i) {
     if (global_id[i] < 0 || global_id[i] > 0xfffffff0ll || (i > 0 && global_id[i] <= global_id[i - 1]))
       return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: global ids must be ascending and unique");
-    const int c = host_cell(px[i], inv_h);
-    if (c < ctx->slab.cut_lo || c >= ctx->slab.cut_hi)
-      return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: a particle lies outside this slab's cuts");
     gid[i] = (uint32_t)global_id[i];
-    pos[i] = make_float4(px[i], py[i], pz[i], 0.0f);
-    vel[i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
   }
+  // A particle outside the cuts is legal input: the next substep migrates it (one hop per slab).
   if (n) {
-    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, vel.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    const float* src[6] = {px, py, pz, vx, vy, vz};
+    for (int a = 0; a < 6; ++a)
+      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->soa[a].p, src[a], n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->slab.gid_o.p, gid.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const float* dsoa[6] = {ctx->soa[0].p, ctx->soa[1].p, ctx->soa[2].p, ctx->soa[3].p, ctx->soa[4].p, ctx->soa[5].p};
+    ctx->launch_count += launch_pack_state(dsoa, ctx->pos_o.p, ctx->vel_o.p, (int)n, ctx->stream);
     PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->n = n;
@@ -639,21 +693,20 @@ int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py, fl
   cudaSetDevice(ctx->device);
   const size_t n = ctx->n;
   if (n == 0) return PBF_OK;
-  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  std::vector<float4> pos(n), vel(n);
-  std::vector<uint32_t> gid(n);
-  PBF_CUDA(ctx, cudaMemcpy(pos.data(), ctx->pos_o.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
-  PBF_CUDA(ctx, cudaMemcpy(vel.data(), ctx->vel_o.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
-  PBF_CUDA(ctx, cudaMemcpy(gid.data(), ctx->slab.gid_o.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < n; ++i) {
-    if (global_id) global_id[i] = (int64_t)gid[i];
-    if (px) px[i] = pos[i].x;
-    if (py) py[i] = pos[i].y;
-    if (pz) pz[i] = pos[i].z;
-    if (vx) vx[i] = vel[i].x;
-    if (vy) vy[i] = vel[i].y;
-    if (vz) vz[i] = vel[i].z;
+  float* dst[6] = {px, py, pz, vx, vy, vz};
+  float* dsoa[6];
+  for (int a = 0; a < 6; ++a) dsoa[a] = dst[a] ? ctx->soa[a].p : nullptr;
+  ctx->launch_count += launch_unpack_state(ctx->pos_o.p, ctx->vel_o.p, dsoa, (int)n, ctx->stream);
+  for (int a = 0; a < 6; ++a)
+    if (dst[a]) PBF_CUDA(ctx, cudaMemcpyAsync(dst[a], ctx->soa[a].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint32_t>& gid = ctx->slab.gid_host;
+  if (global_id) {
+    gid.resize(n);
+    PBF_CUDA(ctx, cudaMemcpyAsync(gid.data(), ctx->slab.gid_o.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (global_id)
+    for (size_t i = 0; i < n; ++i) global_id[i] = (int64_t)gid[i];
   return PBF_OK;
 }
 
@@ -763,6 +816,7 @@ int pbf_debug_set_slab_capacity(pbf_ctx* ctx, int mcap, int gcap) {
   if (!ctx || mcap < 1 || gcap < 1) return PBF_E_INVALID;
   ctx->slab.mcap = mcap;
   ctx->slab.gcap = gcap;
+  ctx->slab.fixed_caps = false;
   return PBF_OK;
 }
 

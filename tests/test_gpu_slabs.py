@@ -74,6 +74,20 @@ def test_virtual_slabs_migration(built):
     grp.close()
 
 
+def test_virtual_slabs_unequal_slabs_share_capacities(built):
+    """fluid_xlarge: slabs hold different particle counts, large enough that the capacity
+    heuristics leave their floor values; the message capacities are wire format and must agree."""
+    params, planes, state = _scene(scenes.SCENES["fluid_xlarge"], H.STABLE_FLAGS)
+    sol = _single(params, planes, state)
+    grp = SlabGroup([0] * 3, params, planes)
+    grp.upload(state)
+    assert len(set(grp.owned())) > 1
+    grp.step(4)
+    sol.step(4)
+    _assert_same(grp, sol, "fluid_xlarge, 3 slabs")
+    grp.close()
+
+
 def test_virtual_slabs_against_oracle(built):
     params, planes, state = _scene(scenes.small_block(12), H.ALL_FLAGS)
     from oracle.oracle_api import Oracle, best_kind
