@@ -37,6 +37,12 @@ namespace {
 #ifndef PBF_PAIR_UNROLL
 #define PBF_PAIR_UNROLL 2
 #endif
+#ifndef PBF_SOLVE_MINBLOCKS
+#define PBF_SOLVE_MINBLOCKS 1
+#endif
+#ifndef PBF_LIST_PREFETCH
+#define PBF_LIST_PREFETCH 1
+#endif
 constexpr int kBlock = PBF_SOLVE_BLOCK;
 constexpr int kPairUnroll = PBF_PAIR_UNROLL;  // neighbour PAIRS fetched per batch (4 independent gathers in flight)
 
@@ -54,6 +60,32 @@ __device__ __forceinline__ void for_each_pair(const uint32_t* __restrict__ nbr_i
   const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
   const uint32_t npairs = cnt >> 1;
   uint32_t p = 0;
+#if PBF_LIST_PREFETCH
+  // the indices of batch p+1 are requested before batch p is gathered: the list streams from
+  // DRAM/L2, and without this every batch pays list latency + gather latency back to back
+  uint2 jn[kPairUnroll];
+  if (kPairUnroll <= npairs) {
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) jn[u] = __ldcs(row + (size_t)u * 32u);
+  }
+  for (; p + kPairUnroll <= npairs; p += kPairUnroll) {
+    uint2 j[kPairUnroll];
+    float4 a0[kPairUnroll], a1[kPairUnroll];
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) j[u] = jn[u];
+    if (p + 2 * kPairUnroll <= npairs) {
+#pragma unroll
+      for (int u = 0; u < kPairUnroll; ++u) jn[u] = __ldcs(row + (size_t)(p + kPairUnroll + u) * 32u);
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      a0[u] = a4[j[u].x];
+      a1[u] = a4[j[u].y];
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], true);
+  }
+#else
   for (; p + kPairUnroll <= npairs; p += kPairUnroll) {
     uint2 j[kPairUnroll];
     float4 a0[kPairUnroll], a1[kPairUnroll];
@@ -67,6 +99,7 @@ __device__ __forceinline__ void for_each_pair(const uint32_t* __restrict__ nbr_i
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], true);
   }
+#endif
   for (; p < npairs; ++p) {
     const uint2 j = __ldcs(row + (size_t)p * 32u);
     const float4 a0 = a4[j.x], a1 = a4[j.y];
@@ -86,6 +119,32 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
   const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
   const uint32_t npairs = cnt >> 1;
   uint32_t p = 0;
+#if PBF_LIST_PREFETCH
+  uint2 jn[kPairUnroll];
+  if (kPairUnroll <= npairs) {
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) jn[u] = __ldcs(row + (size_t)u * 32u);
+  }
+  for (; p + kPairUnroll <= npairs; p += kPairUnroll) {
+    uint2 j[kPairUnroll];
+    float4 a0[kPairUnroll], a1[kPairUnroll], b0[kPairUnroll], b1[kPairUnroll];
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) j[u] = jn[u];
+    if (p + 2 * kPairUnroll <= npairs) {
+#pragma unroll
+      for (int u = 0; u < kPairUnroll; ++u) jn[u] = __ldcs(row + (size_t)(p + kPairUnroll + u) * 32u);
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) {
+      a0[u] = a4[j[u].x];
+      a1[u] = a4[j[u].y];
+      b0[u] = b4[j[u].x];
+      b1[u] = b4[j[u].y];
+    }
+#pragma unroll
+    for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], b0[u], b1[u], true);
+  }
+#else
   for (; p + kPairUnroll <= npairs; p += kPairUnroll) {
     uint2 j[kPairUnroll];
     float4 a0[kPairUnroll], a1[kPairUnroll], b0[kPairUnroll], b1[kPairUnroll];
@@ -101,6 +160,7 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], b0[u], b1[u], true);
   }
+#endif
   for (; p < npairs; ++p) {
     const uint2 j = __ldcs(row + (size_t)p * 32u);
     body(a4[j.x], a4[j.y], b4[j.x], b4[j.y], true);
@@ -111,49 +171,66 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
   }
 }
 
-// ---- 2-wide geometry of a neighbour pair ---------------------------------------------
-template <bool S>
-struct PairGeom {
-  f2 dx, dy, dz, r2;
-  bool in0, in1;  // r2 < h2 (core.cpp:302), and the second neighbour exists
+// ---- per-neighbour geometry -----------------------------------------------------------
+// Instruction-count driven layout (the passes are issue-bound): the x and y
+// components of ONE neighbour are packed into an f32x2 (they already sit in an aligned register
+// pair after the 16-byte gather, so no moves are needed), z stays scalar; the scalar chains that
+// depend only on r2 (poly6, sqrt, spiky) are then evaluated 2-wide over TWO neighbours.
+template <bool S> struct A1;
+template <> struct A1<true> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+};
+template <> struct A1<false> {
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+};
+
+struct NGeom {
+  f2 dxy;    // (xi - xj, yi - yj)
+  float dz;  // zi - zj
+  float r2;  // (dx*dx + dy*dy) + dz*dz (core.cpp:299)
 };
 
 template <bool S>
-__device__ __forceinline__ PairGeom<S> pair_geom(float xi, float yi, float zi, float4 a0, float4 a1, bool v1,
-                                                 const StepConsts& c) {
+__device__ __forceinline__ NGeom ngeom(f2 pxy, float pz, float4 a) {
   using M = M2<S>;
-  PairGeom<S> g;
-  g.dx = M::sub(bcast(xi), make_float2(a0.x, a1.x));
-  g.dy = M::sub(bcast(yi), make_float2(a0.y, a1.y));
-  g.dz = M::sub(bcast(zi), make_float2(a0.z, a1.z));
-  g.r2 = M::addp(M::addp(M::mul(g.dx, g.dx), M::mul(g.dy, g.dy)), M::mul(g.dz, g.dz));  // core.cpp:299
-  g.in0 = g.r2.x < c.h2;
-  g.in1 = v1 && (g.r2.y < c.h2);
+  using A = A1<S>;
+  NGeom g;
+  g.dxy = M::sub(pxy, make_float2(a.x, a.y));
+  g.dz = A::sub(pz, a.z);
+  const f2 sq = M::mul(g.dxy, g.dxy);
+  g.r2 = A::add(A::add(sq.x, sq.y), A::mul(g.dz, g.dz));
   return g;
 }
 
-// poly6_kernel (core.cpp:35-46) on two r2 values: 0 if r2 > h2 else coeff * ((diff*diff)*diff)
-template <bool S>
+// poly6_kernel (core.cpp:35-46) on two r2 values: coeff * ((diff*diff)*diff), 0 if r2 > h2.
+// CLAMP: the "0 if r2 > h2" branch as max(diff, 0) — coeff * 0 is the same +0 the branch returns
+// (and r2 == h2 gives coeff * 0 in the reference as well).  Callers that only use the value under
+// r2 < h2 skip the clamp.
+template <bool S, bool CLAMP>
 __device__ __forceinline__ f2 poly6_2(f2 r2, const StepConsts& c) {
   using M = M2<S>;
-  const f2 diff = M::sub(bcast(c.h2), r2);
-  f2 w = M::mul(bcast(c.poly6_coeff), M::mul(M::mul(diff, diff), diff));
-  if (r2.x > c.h2) w.x = 0.0f;
-  if (r2.y > c.h2) w.y = 0.0f;
-  return w;
+  f2 diff = M::sub(bcast(c.h2), r2);
+  if (CLAMP) diff = make_float2(fmaxf(diff.x, 0.0f), fmaxf(diff.y, 0.0f));
+  return M::mul(bcast(c.poly6_coeff), M::mul(M::mul(diff, diff), diff));
 }
 
-// spiky_gradient_factor(sqrt(max(r2, min_r2))) (core.cpp:48-57, 303-304) on two r2 values
+// spiky_gradient_factor(sqrt(max(r2, min_r2))) (core.cpp:48-57, 303-304) on two r2 values:
+// (coeff * diff) * diff with diff = h - r.  Only used under r2 < h2; the reference's "0 if r > h"
+// can then only trigger through rounding at r2 ~ h2, and max(diff, 0) reproduces it up to the
+// sign of a zero that is added to an accumulator (x + -0 == x + +0 for every x but -0, and the
+// accumulators start at +0 and can never become -0).
 template <bool S>
 __device__ __forceinline__ f2 spiky_2(f2 r2, const StepConsts& c) {
   using M = M2<S>;
-  const f2 rc = make_float2(r2.x < c.min_r2 ? c.min_r2 : r2.x, r2.y < c.min_r2 ? c.min_r2 : r2.y);
+  const f2 rc = make_float2(fmaxf(r2.x, c.min_r2), fmaxf(r2.y, c.min_r2));
   const f2 r = M::sqrt(rc, c.sqrt_safe != 0);
-  const f2 diff = M::sub(bcast(c.h), r);
-  f2 gf = M::mul(M::mul(bcast(c.spiky_coeff), diff), diff);
-  if (r.x > c.h) gf.x = 0.0f;
-  if (r.y > c.h) gf.y = 0.0f;
-  return gf;
+  f2 diff = M::sub(bcast(c.h), r);
+  diff = make_float2(fmaxf(diff.x, 0.0f), fmaxf(diff.y, 0.0f));
+  return M::mul(M::mul(bcast(c.spiky_coeff), diff), diff);
 }
 
 // pow_ratio_n (core.cpp:59-71)
@@ -199,7 +276,7 @@ __device__ __forceinline__ void finalize_particle(float4 pos, V3<F> v, uint32_t 
 
 // ---------------------------------------------------------------- a8 lambda
 template <bool S>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
          const StatusBlock* st, DebugPtrs dbg, int K, NRef nr) {
@@ -211,27 +288,45 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
   if (i >= n) return;
   const float4 pi = pred[i];
   float rho = 0.0f, gsx = 0.0f, gsy = 0.0f, gsz = 0.0f, sum_grad2 = 0.0f;
-  const f2 neg_scale = bcast(-c.grad_scale);
+  using A = A1<S>;
+  const f2 pxy = make_float2(pi.x, pi.y);
+  const float neg_scale = -c.grad_scale;
   for_each_pair(nbr_idx, K, i, nbr_count[i], pred, [&](float4 a0, float4 a1, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
-    const f2 w = poly6_2<S>(g.r2, c);                     // rho += poly6(r2) (core.cpp:300)
-    const f2 gf = spiky_2<S>(g.r2, c);
-    const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
-    const f2 jx = M::mul(neg_scale, gx), jy = M::mul(neg_scale, gy), jz = M::mul(neg_scale, gz);
-    const f2 t = M::addp(M::addp(M::mul(jx, jx), M::mul(jy, jy)), M::mul(jz, jz));  // core.cpp:314-315
-    rho = M::adds(rho, w.x);
-    if (g.in0) {
-      gsx = M::adds(gsx, gx.x);
-      gsy = M::adds(gsy, gy.x);
-      gsz = M::adds(gsz, gz.x);
-      sum_grad2 = M::adds(sum_grad2, t.x);
+    const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
+    const f2 r2 = make_float2(g0.r2, g1.r2);
+    f2 w = poly6_2<S, true>(r2, c);                        // rho += poly6(r2) (core.cpp:300)
+    f2 gf = spiky_2<S>(r2, c);
+    // Straight-line code instead of two divergent branches: a neighbour that fails r2 < h2
+    // (core.cpp:302) gets grad_factor = 0, so every term it adds below is a +-0 — a no-op on
+    // accumulators that start at +0 (they can never hold -0).  Same for the odd tail slot.
+    gf.x = (g0.r2 < c.h2) ? gf.x : 0.0f;
+    gf.y = (v1 && g1.r2 < c.h2) ? gf.y : 0.0f;
+    if (!v1) w.y = 0.0f;
+    {
+      const f2 gxy = M::mul(g0.dxy, bcast(gf.x));
+      const float gz = A::mul(gf.x, g0.dz);
+      const f2 jxy = M::mul(bcast(neg_scale), gxy);
+      const float jz = A::mul(neg_scale, gz);
+      const f2 jj = M::mul(jxy, jxy);
+      const float t = A::add(A::add(jj.x, jj.y), A::mul(jz, jz));
+      rho = M::adds(rho, w.x);
+      gsx = M::adds(gsx, gxy.x);
+      gsy = M::adds(gsy, gxy.y);
+      gsz = M::adds(gsz, gz);
+      sum_grad2 = M::adds(sum_grad2, t);
     }
-    if (v1) rho = M::adds(rho, w.y);
-    if (g.in1) {
-      gsx = M::adds(gsx, gx.y);
-      gsy = M::adds(gsy, gy.y);
-      gsz = M::adds(gsz, gz.y);
-      sum_grad2 = M::adds(sum_grad2, t.y);
+    {
+      const f2 gxy = M::mul(g1.dxy, bcast(gf.y));
+      const float gz = A::mul(gf.y, g1.dz);
+      const f2 jxy = M::mul(bcast(neg_scale), gxy);
+      const float jz = A::mul(neg_scale, gz);
+      const f2 jj = M::mul(jxy, jxy);
+      const float t = A::add(A::add(jj.x, jj.y), A::mul(jz, jz));
+      rho = M::adds(rho, w.y);
+      gsx = M::adds(gsx, gxy.x);
+      gsy = M::adds(gsy, gxy.y);
+      gsz = M::adds(gsz, gz);
+      sum_grad2 = M::adds(sum_grad2, t);
     }
   });
   // core.cpp:319-328
@@ -253,7 +348,7 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
 // ---------------------------------------------------------------- a9 + a10 (+ a11, a14)
 // LAST: also velocity update / commit; is_final: additionally restitution + scatter.
 template <bool S, bool LAST>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
         const float4* __restrict__ pos_s, const float* __restrict__ rho, float4* __restrict__ vel_out,
@@ -267,28 +362,29 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
   if (i >= n) return;
   const float4 pi = pred_in[i];
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  using A = A1<S>;
+  const f2 pxy = make_float2(pi.x, pi.y);
   for_each_pair(nbr_idx, K, i, nbr_count[i], pred_in, [&](float4 a0, float4 a1, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
-    const f2 gf = spiky_2<S>(g.r2, c);
-    f2 s = M::add(bcast(pi.w), make_float2(a0.w, a1.w));  // lambda_i + lambda_j (core.cpp:355)
+    const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
+    const f2 r2 = make_float2(g0.r2, g1.r2);
+    const f2 gf = spiky_2<S>(r2, c);
+    f2 s = make_float2(A::add(pi.w, a0.w), A::add(pi.w, a1.w));  // lambda_i + lambda_j (core.cpp:355)
     if (c.scorr_on) {                                      // core.cpp:356-361
-      const f2 w = poly6_2<S>(g.r2, c);
+      const f2 w = poly6_2<S, false>(r2, c);
       const f2 ratio = M::mul(w, bcast(c.scorr_inv_wdq));
       const f2 corr = M::mul(bcast(c.scorr_negk), pow_ratio_2<S>(ratio, c.scorr_n));
       s = M::addp(s, corr);
     }
-    const f2 sg = M::mul(s, gf);                           // (s * grad_factor) * d (core.cpp:362-364)
-    const f2 tx = M::mul(sg, g.dx), ty = M::mul(sg, g.dy), tz = M::mul(sg, g.dz);
-    if (g.in0) {
-      sx = M::adds(sx, tx.x);
-      sy = M::adds(sy, ty.x);
-      sz = M::adds(sz, tz.x);
-    }
-    if (g.in1) {
-      sx = M::adds(sx, tx.y);
-      sy = M::adds(sy, ty.y);
-      sz = M::adds(sz, tz.y);
-    }
+    f2 sg = M::mul(s, gf);                                 // (s * grad_factor) * d (core.cpp:362-364)
+    sg.x = (g0.r2 < c.h2) ? sg.x : 0.0f;                   // outside h: the terms below are +-0 (no-ops)
+    sg.y = (v1 && g1.r2 < c.h2) ? sg.y : 0.0f;
+    const f2 t0 = M::mul(g0.dxy, bcast(sg.x)), t1 = M::mul(g1.dxy, bcast(sg.y));
+    sx = M::adds(sx, t0.x);
+    sy = M::adds(sy, t0.y);
+    sz = M::adds(sz, A::mul(sg.x, g0.dz));
+    sx = M::adds(sx, t1.x);
+    sy = M::adds(sy, t1.y);
+    sz = M::adds(sz, A::mul(sg.y, g1.dz));
   });
   const F xi(pi.x), yi(pi.y), zi(pi.z);
   F ax(sx), ay(sy), az(sz);
@@ -335,7 +431,7 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
 
 // ---------------------------------------------------------------- a12 XSPH
 template <bool S>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4* __restrict__ vel_out,
        const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
        const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
@@ -350,25 +446,23 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
   const float4 pi = pos[i];
   const float4 vi = vel_in[i];
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  using A = A1<S>;
+  const f2 pxy = make_float2(pi.x, pi.y), vxy = make_float2(vi.x, vi.y);
   for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel_in,
                  [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
-    const f2 w = poly6_2<S>(g.r2, c);
-    const f2 inv_rho = make_float2(b0.w, b1.w);
+    const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
+    f2 w = poly6_2<S, false>(make_float2(g0.r2, g1.r2), c);
+    w.x = (g0.r2 < c.h2) ? w.x : 0.0f;                     // outside h: the terms below are +-0 (no-ops)
+    w.y = (v1 && g1.r2 < c.h2) ? w.y : 0.0f;
     // ((v_j - v_i) * W) * inv_rho_j (core.cpp:449-451)
-    const f2 tx = M::mul(M::mul(M::sub(make_float2(b0.x, b1.x), bcast(vi.x)), w), inv_rho);
-    const f2 ty = M::mul(M::mul(M::sub(make_float2(b0.y, b1.y), bcast(vi.y)), w), inv_rho);
-    const f2 tz = M::mul(M::mul(M::sub(make_float2(b0.z, b1.z), bcast(vi.z)), w), inv_rho);
-    if (g.in0) {
-      sx = M::adds(sx, tx.x);
-      sy = M::adds(sy, ty.x);
-      sz = M::adds(sz, tz.x);
-    }
-    if (g.in1) {
-      sx = M::adds(sx, tx.y);
-      sy = M::adds(sy, ty.y);
-      sz = M::adds(sz, tz.y);
-    }
+    const f2 t0 = M::mul(M::mul(M::sub(make_float2(b0.x, b0.y), vxy), bcast(w.x)), bcast(b0.w));
+    const f2 t1 = M::mul(M::mul(M::sub(make_float2(b1.x, b1.y), vxy), bcast(w.y)), bcast(b1.w));
+    sx = M::adds(sx, t0.x);
+    sy = M::adds(sy, t0.y);
+    sz = M::adds(sz, A::mul(A::mul(A::sub(b0.z, vi.z), w.x), b0.w));
+    sx = M::adds(sx, t1.x);
+    sy = M::adds(sy, t1.y);
+    sz = M::adds(sz, A::mul(A::mul(A::sub(b1.z, vi.z), w.y), b1.w));
   });
   if (dbg.dv) dbg.dv[i] = make_float4(sx, sy, sz, 0.0f);
   V3<F> v;  // core.cpp:461-465
@@ -384,7 +478,7 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
 
 // ---------------------------------------------------------------- a13 vorticity, pass 1
 template <bool S>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* __restrict__ omega,
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count, StepConsts c,
              const StatusBlock* st, int K, NRef nr) {
@@ -397,27 +491,28 @@ k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* _
   const float4 pi = pos[i];
   const float4 vi = vel[i];
   float ox = 0.0f, oy = 0.0f, oz = 0.0f;
+  using A = A1<S>;
+  const f2 pxy = make_float2(pi.x, pi.y), vxy = make_float2(vi.x, vi.y);
+  auto one = [&](const NGeom& g, float gf, float4 b) {     // core.cpp:493-504
+    const f2 gxy = M::mul(g.dxy, bcast(gf));
+    const float gz = A::mul(gf, g.dz);
+    const f2 uxy = M::sub(make_float2(b.x, b.y), vxy);
+    const float uz = A::sub(b.z, vi.z);
+    const float tx = A::sub(A::mul(uxy.y, gz), A::mul(uz, gxy.y));   // core.cpp:499-501
+    const float ty = A::sub(A::mul(uz, gxy.x), A::mul(uxy.x, gz));
+    const float tz = A::sub(A::mul(uxy.x, gxy.y), A::mul(uxy.y, gxy.x));
+    ox = M::adds(ox, tx);
+    oy = M::adds(oy, ty);
+    oz = M::adds(oz, tz);
+  };
   for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel,
                  [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
-    const f2 gf = spiky_2<S>(g.r2, c);
-    const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
-    const f2 ux = M::sub(make_float2(b0.x, b1.x), bcast(vi.x));
-    const f2 uy = M::sub(make_float2(b0.y, b1.y), bcast(vi.y));
-    const f2 uz = M::sub(make_float2(b0.z, b1.z), bcast(vi.z));
-    const f2 tx = M::subp(M::mul(uy, gz), M::mul(uz, gy));  // core.cpp:499-501
-    const f2 ty = M::subp(M::mul(uz, gx), M::mul(ux, gz));
-    const f2 tz = M::subp(M::mul(ux, gy), M::mul(uy, gx));
-    if (g.in0) {
-      ox = M::adds(ox, tx.x);
-      oy = M::adds(oy, ty.x);
-      oz = M::adds(oz, tz.x);
-    }
-    if (g.in1) {
-      ox = M::adds(ox, tx.y);
-      oy = M::adds(oy, ty.y);
-      oz = M::adds(oz, tz.y);
-    }
+    const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
+    f2 gf = spiky_2<S>(make_float2(g0.r2, g1.r2), c);
+    gf.x = (g0.r2 < c.h2) ? gf.x : 0.0f;                   // outside h: every term is +-0 (a no-op)
+    gf.y = (v1 && g1.r2 < c.h2) ? gf.y : 0.0f;
+    one(g0, gf.x, b0);
+    one(g1, gf.y, b1);
   });
   const F fx(ox), fy(oy), fz(oz);
   float m = __fsqrt_rn(Arith<F>::val(fx * fx + fy * fy + fz * fz));  // core.cpp:507
@@ -428,7 +523,7 @@ k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* _
 
 // ---------------------------------------------------------------- a13 pass 2 + apply (+ a14)
 template <bool S>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ omega,
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
              const float4* __restrict__ pos_s, const float4* __restrict__ planes,
@@ -442,22 +537,24 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   if (i >= n) return;
   const float4 pi = pos[i];
   float ex = 0.0f, ey = 0.0f, ez = 0.0f;
+  using A = A1<S>;
+  const f2 pxy = make_float2(pi.x, pi.y);
+  auto one = [&](const NGeom& g, float gf, float wj) {     // core.cpp:528-538
+    const f2 gxy = M::mul(g.dxy, bcast(gf));
+    const float gz = A::mul(gf, g.dz);
+    const float coeff = A::sub(wj, pi.w);                  // |omega_j| - |omega_i| (core.cpp:534)
+    const f2 txy = M::mul(bcast(coeff), gxy);
+    ex = M::adds(ex, txy.x);
+    ey = M::adds(ey, txy.y);
+    ez = M::adds(ez, A::mul(coeff, gz));
+  };
   for_each_pair(nbr_idx, K, i, nbr_count[i], pos, [&](float4 a0, float4 a1, bool v1) {
-    const PairGeom<S> g = pair_geom<S>(pi.x, pi.y, pi.z, a0, a1, v1, c);
-    const f2 gf = spiky_2<S>(g.r2, c);
-    const f2 gx = M::mul(gf, g.dx), gy = M::mul(gf, g.dy), gz = M::mul(gf, g.dz);
-    const f2 coeff = M::sub(make_float2(a0.w, a1.w), bcast(pi.w));  // |omega_j| - |omega_i| (core.cpp:534)
-    const f2 tx = M::mul(coeff, gx), ty = M::mul(coeff, gy), tz = M::mul(coeff, gz);
-    if (g.in0) {
-      ex = M::adds(ex, tx.x);
-      ey = M::adds(ey, ty.x);
-      ez = M::adds(ez, tz.x);
-    }
-    if (g.in1) {
-      ex = M::adds(ex, tx.y);
-      ey = M::adds(ey, ty.y);
-      ez = M::adds(ez, tz.y);
-    }
+    const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
+    f2 gf = spiky_2<S>(make_float2(g0.r2, g1.r2), c);
+    gf.x = (g0.r2 < c.h2) ? gf.x : 0.0f;                   // outside h: every term is +-0 (a no-op)
+    gf.y = (v1 && g1.r2 < c.h2) ? gf.y : 0.0f;
+    one(g0, gf.x, a0.w);
+    one(g1, gf.y, a1.w);
   });
   if (dbg.eta) dbg.eta[i] = make_float4(ex, ey, ez, 0.0f);
   // core.cpp:547-570
@@ -485,7 +582,7 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
 
 // solver_iterations == 0: core.cpp:277 never runs, pred is committed as predicted.
 template <bool S>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
               const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
               StepConsts c, const StatusBlock* st, NRef nr) {
