@@ -25,7 +25,6 @@ namespace pbf {
 namespace {
 
 constexpr int kThreads = 256;
-
 // ---------------------------------------------------------------- state (de)interleave
 __global__ void __launch_bounds__(kThreads)
 k_pack_state(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
@@ -421,13 +420,11 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
       }
     nbr_count[i] = cnt < (uint32_t)K ? cnt : (uint32_t)K;
   }
-  // batch statistics: max count (to size K) and the total (debug)
+  // batch statistic: max count (to size K)
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, cnt);
-  const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt);
   if ((threadIdx.x & 31) == 0) {
     if (wmax > *(volatile unsigned int*)&st->max_neighbors) atomicMax(&st->max_neighbors, wmax);
     if (wmax > (uint32_t)K) st->nbr_overflow = 1;
-    atomicAdd(&st->total_neighbors, (unsigned long long)wsum);
   }
 }
 

@@ -616,7 +616,14 @@ int pbf_debug_sizes(pbf_ctx* ctx, size_t* ncells, size_t* nneighbors) {
   if (!ctx) return PBF_E_INVALID;
   cudaSetDevice(ctx->device);
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (nneighbors) *nneighbors = (size_t)ctx->last_status.total_neighbors;
+  if (nneighbors) {  // sum of the per-particle counts of the last substep
+    std::vector<uint32_t> counts;
+    int rc = fetch(ctx, counts, ctx->nbr_count.p, ctx->n);
+    if (rc != PBF_OK) return rc;
+    size_t total = 0;
+    for (uint32_t c : counts) total += c;
+    *nneighbors = total;
+  }
   if (ncells) {
     size_t occupied = 0;
     if (ctx->n) {
