@@ -158,6 +158,7 @@ ABI = {
     "pbf_slab_owned": (C.c_size_t, [C.c_void_p]),
     "pbf_slab_download": (C.c_int, [C.c_void_p, _i64p] + [_f32p] * 6),
     "pbf_slab_upload_owned": (C.c_int, [C.c_void_p, C.c_size_t, _i64p] + [_f32p] * 6),
+    "pbf_slab_set_p2p": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
     "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
     "pbf_slab_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32p, _i32p]),
@@ -374,6 +375,9 @@ class SlabSolver(Solver):
         self._check(self.lib.pbf_slab_upload_owned(self.ctx, gid.shape[0], gid.ctypes.data_as(_i64p),
                                                    *[fptr(a) for a in arrs]))
 
+    def set_p2p(self, enabled: bool):
+        self._check(self.lib.pbf_slab_set_p2p(self.ctx, int(enabled)))
+
     def owned(self) -> int:
         return int(self.lib.pbf_slab_owned(self.ctx))
 
@@ -406,7 +410,8 @@ class SlabGroup:
     "virtual ranks" (the 1-GPU parity tests), contexts on different devices a single-process
     multi-GPU run."""
 
-    def __init__(self, devices, params: PbfParams, planes: np.ndarray, mode: int = PBF_MODE_STRICT):
+    def __init__(self, devices, params: PbfParams, planes: np.ndarray, mode: int = PBF_MODE_STRICT,
+                 p2p: bool = False):
         self.lib = load_library()
         self.slabs = [SlabSolver(d, 0, mode) for d in devices]
         for s in self.slabs:
@@ -416,6 +421,9 @@ class SlabGroup:
         self.group = self.lib.pbf_group_create(arr, len(self.slabs))
         if not self.group:
             raise PbfError("pbf_group_create failed")
+        if p2p:
+            for s in self.slabs:
+                s.set_p2p(True)
         self.n = 0
 
     def _check(self, rc: int):

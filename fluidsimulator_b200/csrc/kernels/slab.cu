@@ -108,7 +108,8 @@ k_slab_scan(uint32_t* __restrict__ blk_cnt, SlabCounts* __restrict__ counts, Sta
         if (total > mcap) st->mig_overflow = 1;
         atomicMax(&st->max_send, (unsigned int)total);
         float4* msg = (c == 1) ? send_l : send_r;
-        msg[0] = hdr_make(total > mcap ? mcap : total);
+        // an overflowing message is never packed (the batch is replayed): tell the receiver so
+        msg[0] = total > mcap ? hdr_fail() : hdr_make(total);
       }
     }
     __syncthreads();
@@ -270,9 +271,12 @@ __global__ void k_slab_bounds(const uint32_t* __restrict__ keys, const GridDesc*
   }
   const int worst = b0 > b1 ? b0 : b1;
   atomicMax(&st->max_ghost, (unsigned int)worst);
-  if (worst > gcap) st->ghost_overflow = 1;
-  b0 = b0 > gcap ? gcap : b0;
-  b1 = b1 > gcap ? gcap : b1;
+  if (worst > gcap) {  // never packed (the batch is replayed): tell the receivers so
+    st->ghost_overflow = 1;
+    counts->b[0] = counts->b[1] = 0;
+    send_l[0] = send_r[0] = hdr_fail();
+    return;
+  }
   counts->b[0] = b0;
   counts->b[1] = b1;
   send_l[0] = hdr_make(b0);

@@ -60,6 +60,17 @@ struct Transport {
   virtual void abort() {}
   // true when exchange() is purely stream-ordered, i.e. may be recorded into a CUDA graph
   virtual bool capturable() const { return false; }
+  // Called at the start of every slab batch attempt, before anything is enqueued: (re)establish
+  // what the transport needs for messages of `msg_elems` float4.  Collective when it has to talk
+  // to the neighbours (every rank reaches it with the same msg_elems).
+  virtual int prepare(pbf_ctx* ctx, size_t msg_elems) { (void)ctx; (void)msg_elems; return PBF_OK; }
+  // Buffers of exchange number `index` out of `count` per substep: where the pack kernels write
+  // the two outgoing messages and where the incoming ones will be found.  Returns false when the
+  // transport has no opinion (the context's own send/recv buffers are used).
+  virtual bool bind(pbf_ctx* ctx, int index, int count, float4* send[2], float4* recv[2]) {
+    (void)ctx; (void)index; (void)count; (void)send; (void)recv;
+    return false;
+  }
 };
 
 struct SlabState {
@@ -77,6 +88,7 @@ struct SlabState {
   uint64_t graph_exchanges = 0, graph_bytes = 0;  // per replay of the captured substep
   bool warm = false;                       // a batch has completed since the communicator was joined
   bool fixed_caps = false;                 // keep the message capacities (no adaptive shrinking)
+  int want_p2p = -1;                       // direct peer stores instead of messages: -1 = default for the transport
   Transport* transport = nullptr;          // not owned when it belongs to a group
   bool owns_transport = false;
   DevBuf<SlabCounts> counts;

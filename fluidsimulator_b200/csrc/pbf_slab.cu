@@ -9,6 +9,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -85,21 +86,27 @@ namespace {
 struct NcclTransport : Transport {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  int repeat = 1;
+  NcclTransport() {
+    if (const char* e = std::getenv("PBF_SLAB_EXCHANGE_REPEAT")) repeat = std::max(1, std::atoi(e));
+  }
   ~NcclTransport() override {
     if (comm) ncclCommDestroy(comm);
   }
   int exchange(pbf_ctx* ctx, float4* const send[2], float4* const recv[2], size_t bytes) override {
     if (nranks == 1) return PBF_OK;
-    PBF_NCCL(ctx, ncclGroupStart());
-    if (rank > 0) {
-      PBF_NCCL(ctx, ncclSend(send[0], bytes, ncclChar, rank - 1, comm, ctx->stream));
-      PBF_NCCL(ctx, ncclRecv(recv[0], bytes, ncclChar, rank - 1, comm, ctx->stream));
+    for (int rep = 0; rep < repeat; ++rep) {  // repeat > 1: measurement aid (PBF_SLAB_EXCHANGE_REPEAT)
+      PBF_NCCL(ctx, ncclGroupStart());
+      if (rank > 0) {
+        PBF_NCCL(ctx, ncclSend(send[0], bytes, ncclChar, rank - 1, comm, ctx->stream));
+        PBF_NCCL(ctx, ncclRecv(recv[0], bytes, ncclChar, rank - 1, comm, ctx->stream));
+      }
+      if (rank + 1 < nranks) {
+        PBF_NCCL(ctx, ncclSend(send[1], bytes, ncclChar, rank + 1, comm, ctx->stream));
+        PBF_NCCL(ctx, ncclRecv(recv[1], bytes, ncclChar, rank + 1, comm, ctx->stream));
+      }
+      PBF_NCCL(ctx, ncclGroupEnd());
     }
-    if (rank + 1 < nranks) {
-      PBF_NCCL(ctx, ncclSend(send[1], bytes, ncclChar, rank + 1, comm, ctx->stream));
-      PBF_NCCL(ctx, ncclRecv(recv[1], bytes, ncclChar, rank + 1, comm, ctx->stream));
-    }
-    PBF_NCCL(ctx, ncclGroupEnd());
     return PBF_OK;
   }
   int reduce_status_device(pbf_ctx* ctx, unsigned int* dev_words, int count) override {
@@ -126,6 +133,7 @@ struct pbf_group {
   std::vector<cudaEvent_t> packed;                 // per rank
   std::vector<float4*> send_ptr[2];                // [side][rank], published per exchange
   std::vector<std::vector<unsigned int>> words;    // status agreement
+  std::vector<float4*> window;                     // peer windows (direct-store transport)
   // global ids for upload / download
   size_t n_global = 0;
 
@@ -188,6 +196,183 @@ struct LocalTransport : Transport {
   void abort() override { group->abort(); }
 };
 
+
+// ---- direct peer stores + flags ------------------------------------------------------------------
+// The fused transport: no message copy and no collective library on the substep
+// path.  Every rank owns a "window" — a mailbox and three incoming-message buffers per side — that
+// its x-neighbours map (cudaIpc between processes, plain pointers inside one process).  The pack
+// kernels of kernels/slab.cu store boundary data STRAIGHT INTO THE NEIGHBOUR'S WINDOW over NVLink;
+// an exchange is then one tiny kernel that publishes an epoch in both neighbours' mailboxes and
+// spins until both neighbours have published theirs.  Everything is stream-ordered, so the whole
+// substep, halo traffic included, replays as one CUDA graph.
+//   * buffer of exchange i: i & 1, except the last exchange of a substep with an odd count, which
+//     uses buffer 2 — consecutive exchanges never share a buffer, so a sender can never overwrite a
+//     message its neighbour has not unpacked yet (the neighbour's signal for exchange i+1 is only
+//     sent after it unpacked exchange i);
+//   * epochs come from a device-side counter: replaying the graph needs no patched parameters.
+struct PeerMailbox {
+  unsigned int arrived[2];  // epoch last published by the left / right neighbour
+  unsigned int epoch;       // exchanges this rank has started
+  unsigned int pad;
+};
+constexpr size_t kMailboxElems = 16;  // float4 elements reserved for the mailbox (256 B)
+
+__global__ void k_peer_signal_wait(PeerMailbox* mine, PeerMailbox* left, PeerMailbox* right, StatusBlock* st,
+                                   long long timeout_cycles) {
+  // All stores of the preceding pack kernel are complete (kernel boundary); the fences order them
+  // before the flags at system scope.  Runs even when the batch has failed: a neighbour must never
+  // be left waiting.
+  const unsigned int e = mine->epoch + 1u;
+  mine->epoch = e;
+  __threadfence_system();
+  if (left) *reinterpret_cast<volatile unsigned int*>(&left->arrived[1]) = e;    // I am its right neighbour
+  if (right) *reinterpret_cast<volatile unsigned int*>(&right->arrived[0]) = e;  // I am its left neighbour
+  __threadfence_system();
+  const long long t0 = clock64();
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? left : right)) continue;
+    const volatile unsigned int* flag = &mine->arrived[side];
+    while ((int)(*flag - e) < 0) {
+      if (clock64() - t0 > timeout_cycles) {  // the neighbour died or diverged: fail the batch, do not hang
+        st->peer_failed = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+struct PeerTransport : Transport {
+  Transport* inner = nullptr;     // owned: status agreement, rendezvous, abort
+  pbf_group* group = nullptr;     // in-process rendezvous ...
+  NcclTransport* nccl = nullptr;  // ... or IPC handles through the communicator
+  float4* win = nullptr;
+  size_t elems = 0;               // capacity of one message buffer
+  bool dirty = true;              // neighbours do not know the current window yet
+  float4* remote[2] = {nullptr, nullptr};
+  bool ipc_open[2] = {false, false};
+  void* stage = nullptr;          // 3 IPC handles: mine, from left, from right
+  // The first batch after enabling runs through the inner (message) transport: it loads every
+  // kernel and performs every allocation while no rank is spinning on a flag.  That matters when
+  // several slabs share one GPU or one process (virtual ranks): a lazy module load or cudaMalloc
+  // on behalf of one slab synchronises the device and would never return while another slab's
+  // flag kernel waits for it.
+  bool active = false;
+
+  ~PeerTransport() override {
+    close_remote();
+    if (win) cudaFree(win);
+    if (stage) cudaFree(stage);
+    delete inner;
+  }
+  void close_remote() {
+    for (int side = 0; side < 2; ++side) {
+      if (ipc_open[side] && remote[side]) cudaIpcCloseMemHandle(remote[side]);
+      remote[side] = nullptr;
+      ipc_open[side] = false;
+    }
+  }
+  static int buffer_of(int index, int count) { return (index == count - 1 && (count & 1)) ? 2 : (index & 1); }
+  float4* slot(float4* base, int buf, int side) const { return base + kMailboxElems + ((size_t)buf * 2 + (size_t)side) * elems; }
+
+  int prepare(pbf_ctx* ctx, size_t msg_elems) override {
+    const int r = ctx->slab.rank, nr = ctx->slab.nranks;
+    int rc = inner->prepare(ctx, msg_elems);
+    if (rc != PBF_OK) return rc;
+    rc = prepare_window(ctx, msg_elems, r, nr);
+    if (rc != PBF_OK) return rc;
+    active = ctx->slab.warm;
+    // all host-side preparation of every slab is done before any slab may start spinning
+    if (group && !group->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    return PBF_OK;
+  }
+
+  int prepare_window(pbf_ctx* ctx, size_t msg_elems, int r, int nr) {
+    if (!win || msg_elems > elems) {
+      // every rank grows at the same time: capacities are decided on max-reduced statistics
+      PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      close_remote();
+      if (win) cudaFree(win);
+      win = nullptr;
+      const size_t total = kMailboxElems + 6 * msg_elems;
+      PBF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&win), total * sizeof(float4)));
+      PBF_CUDA(ctx, cudaMemset(win, 0, total * sizeof(float4)));
+      elems = msg_elems;
+      dirty = true;
+      invalidate_graph(ctx);
+      cudaFuncAttributes attr;  // forces the (lazily loaded) flag kernel into the context now
+      PBF_CUDA(ctx, cudaFuncGetAttributes(&attr, k_peer_signal_wait));
+    }
+    if (!dirty) return PBF_OK;
+    if (group) {
+      group->window[(size_t)r] = win;
+      if (!group->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+      remote[0] = r > 0 ? group->window[(size_t)r - 1] : nullptr;
+      remote[1] = r + 1 < nr ? group->window[(size_t)r + 1] : nullptr;
+      if (!group->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    } else if (nccl && nr > 1) {
+      cudaIpcMemHandle_t h[3];
+      std::memset(h, 0, sizeof(h));
+      PBF_CUDA(ctx, cudaIpcGetMemHandle(&h[0], win));
+      if (!stage) PBF_CUDA(ctx, cudaMalloc(&stage, sizeof(h)));
+      PBF_CUDA(ctx, cudaMemcpyAsync(stage, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+      char* d = static_cast<char*>(stage);
+      const size_t hb = sizeof(cudaIpcMemHandle_t);
+      PBF_NCCL(ctx, ncclGroupStart());
+      if (r > 0) {
+        PBF_NCCL(ctx, ncclSend(d, hb, ncclChar, r - 1, nccl->comm, ctx->stream));
+        PBF_NCCL(ctx, ncclRecv(d + hb, hb, ncclChar, r - 1, nccl->comm, ctx->stream));
+      }
+      if (r + 1 < nr) {
+        PBF_NCCL(ctx, ncclSend(d, hb, ncclChar, r + 1, nccl->comm, ctx->stream));
+        PBF_NCCL(ctx, ncclRecv(d + 2 * hb, hb, ncclChar, r + 1, nccl->comm, ctx->stream));
+      }
+      PBF_NCCL(ctx, ncclGroupEnd());
+      PBF_CUDA(ctx, cudaMemcpyAsync(h, stage, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int side = 0; side < 2; ++side) {
+        const bool has = side == 0 ? r > 0 : r + 1 < nr;
+        if (!has) continue;
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h[1 + side], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+          return fail(ctx, PBF_E_COMM, std::string("cudaIpcOpenMemHandle (peer window): ") + cudaGetErrorString(e));
+        remote[side] = static_cast<float4*>(ptr);
+        ipc_open[side] = true;
+      }
+    }
+    dirty = false;
+    return PBF_OK;
+  }
+
+  bool bind(pbf_ctx* ctx, int index, int count, float4* send[2], float4* recv[2]) override {
+    if (!active) return inner->bind(ctx, index, count, send, recv);
+    const int buf = buffer_of(index, count);
+    // my message to the left neighbour is what it receives "from the right" (side 1), and vice versa;
+    // without a neighbour the pack kernels write into a local scratch buffer
+    send[0] = remote[0] ? slot(remote[0], buf, 1) : ctx->slab.send[0][0].p;
+    send[1] = remote[1] ? slot(remote[1], buf, 0) : ctx->slab.send[0][1].p;
+    recv[0] = slot(win, buf, 0);
+    recv[1] = slot(win, buf, 1);
+    return true;
+  }
+
+  int exchange(pbf_ctx* ctx, float4* const send[2], float4* const recv[2], size_t bytes) override {
+    if (!active) return inner->exchange(ctx, send, recv, bytes);
+    PeerMailbox* mine = reinterpret_cast<PeerMailbox*>(win);
+    k_peer_signal_wait<<<1, 1, 0, ctx->stream>>>(mine, reinterpret_cast<PeerMailbox*>(remote[0]),
+                                                 reinterpret_cast<PeerMailbox*>(remote[1]), ctx->status.p,
+                                                 4000000000LL);
+    return PBF_OK;
+  }
+  int reduce_status_device(pbf_ctx* ctx, unsigned int* w, int n) override { return inner->reduce_status_device(ctx, w, n); }
+  int reduce_status_host(pbf_ctx* ctx, unsigned int* w, int n) override { return inner->reduce_status_host(ctx, w, n); }
+  void abort() override { inner->abort(); }
+  // Between processes the substep (flag kernels included) replays as a CUDA graph.  Inside one
+  // process graph instantiation by one slab could stall behind another slab's spinning kernel.
+  bool capturable() const override { return group == nullptr && (active || inner->capturable()); }
+};
+
 // ---- buffers -----------------------------------------------------------------------------------
 int ensure_slab_buffers(pbf_ctx* ctx) {
   SlabState& sl = ctx->slab;
@@ -222,10 +407,7 @@ void slab_fill(pbf_ctx* ctx, SlabBuffers& sb) {
   sb.keep_pos = sl.keep_pos.p;
   sb.keep_pred = sl.keep_pred.p;
   sb.blk_cnt = sl.blk_cnt.p;
-  sb.send[0] = sl.send[sl.parity][0].p;
-  sb.send[1] = sl.send[sl.parity][1].p;
-  sb.recv[0] = sl.recv[0].p;
-  sb.recv[1] = sl.recv[1].p;
+  sb.send[0] = sb.send[1] = sb.recv[0] = sb.recv[1] = nullptr;  // slab_bind, per exchange
   sb.cut_lo = sl.cut_lo;
   sb.cut_hi = sl.cut_hi;
   sb.cap = (int)ctx->cap;
@@ -234,7 +416,19 @@ void slab_fill(pbf_ctx* ctx, SlabBuffers& sb) {
   sb.gcap = sl.gcap;
 }
 
-// One exchange with both neighbours; flips the send-buffer parity for the next one.
+// Message buffers of exchange `index` (of `count` per substep), to be called before the kernels
+// that pack it.  Message transports use the context's buffers: the send pair alternates between
+// consecutive exchanges (a neighbour may still be copying the previous message out).
+void slab_bind(pbf_ctx* ctx, SlabBuffers& sb, int index, int count) {
+  SlabState& sl = ctx->slab;
+  if (sl.transport->bind(ctx, index, count, sb.send, sb.recv)) return;
+  sb.send[0] = sl.send[sl.parity][0].p;
+  sb.send[1] = sl.send[sl.parity][1].p;
+  sb.recv[0] = sl.recv[0].p;
+  sb.recv[1] = sl.recv[1].p;
+}
+
+// One exchange with both neighbours.
 int slab_exchange(pbf_ctx* ctx, SlabBuffers& sb, size_t elems) {
   SlabState& sl = ctx->slab;
   stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
@@ -244,8 +438,6 @@ int slab_exchange(pbf_ctx* ctx, SlabBuffers& sb, size_t elems) {
   sl.exchanges++;
   sl.bytes_sent += ((sl.rank > 0) + (sl.rank + 1 < sl.nranks)) * elems * sizeof(float4);
   sl.parity ^= 1;
-  sb.send[0] = sl.send[sl.parity][0].p;
-  sb.send[1] = sl.send[sl.parity][1].p;
   return PBF_OK;
 }
 
@@ -271,6 +463,13 @@ int slab_substep(pbf_ctx* ctx) {
   // A replayed graph bakes the send-buffer pointers in: every substep must start on the same pair.
   // (Stream-ordered transports have no write-after-read hazard on the send buffers.)
   if (sl.transport->capturable()) sl.parity = 0;
+  const int iters = ctx->params.solver_iterations;
+  const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
+  const bool final_in_delta = !tail_xsph && !tail_vort;
+  // exchanges of this substep: migration hops, ghost build, pred refreshes, post-XSPH velocities
+  const int n_ex = sl.hops + 1 + (iters > 0 ? (final_in_delta ? iters - 1 : iters) : 0) +
+                   ((iters > 0 && tail_xsph && tail_vort) ? 1 : 0);
+  int xi = 0;
 
   stage_mark(ctx, PBF_STAGE_PREDICT, 1);
   k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n_own, true, s);
@@ -280,6 +479,7 @@ int slab_substep(pbf_ctx* ctx) {
   // migration: particles whose predicted x-cell left the slab move to the neighbour (hops > 1 only
   // after a batch found a particle more than one slab away)
   for (int hop = 0; hop < sl.hops; ++hop) {
+    slab_bind(ctx, sb, xi++, n_ex);
     k = launch_slab_split(ctx->pos_o.p, ctx->pred_o.p, sb, c, s);
     if ((rc = slab_exchange(ctx, sb, 1 + 2 * (size_t)sl.mcap)) != PBF_OK) return rc;
     k += launch_slab_merge(ctx->pos_o.p, ctx->pred_o.p, sb, c, hop == sl.hops - 1, s);
@@ -301,6 +501,7 @@ int slab_substep(pbf_ctx* ctx) {
   t.launches[PBF_STAGE_CELLS] += k; launches += k;
 
   // ghost build: two boundary layers per side, appended after the owned slots
+  slab_bind(ctx, sb, xi++, n_ex);
   k = launch_slab_ghost_pack(g.keys[out], ctx->pred_a.p, ctx->pos_s.p, g, sb, s);
   if ((rc = slab_exchange(ctx, sb, 1 + 2 * (size_t)sl.gcap)) != PBF_OK) return rc;
   k += launch_slab_ghost_unpack(ctx->pred_a.p, ctx->pos_s.p, g, sb, c, s);
@@ -311,14 +512,11 @@ int slab_substep(pbf_ctx* ctx) {
   stage_mark(ctx, PBF_STAGE_NEIGHBORS, 0);
   t.launches[PBF_STAGE_NEIGHBORS] += k; launches += k;
 
-  const int iters = ctx->params.solver_iterations;
   if (iters <= 0) {
     launches += launch_commit_only(b, c, n_own, strict, s);
     t.launches[PBF_STAGE_FINALIZE] += 1;
     return launches;
   }
-  const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
-  const bool final_in_delta = !tail_xsph && !tail_vort;
   int cur = 0;
   for (int it = 0; it < iters; ++it) {
     const bool last = it == iters - 1;
@@ -332,6 +530,7 @@ int slab_substep(pbf_ctx* ctx) {
     t.launches[PBF_STAGE_DELTA] += 1;
     cur ^= 1;
     if (last && final_in_delta) break;  // nothing reads the ghosts any more
+    slab_bind(ctx, sb, xi++, n_ex);
     k = launch_slab_halo_pack(b.pred[cur], sb, s);
     if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
     k += launch_slab_halo_unpack(b.pred[cur], sb, s);
@@ -350,6 +549,7 @@ int slab_substep(pbf_ctx* ctx) {
     t.launches[PBF_STAGE_XSPH] += 1;
     vcur = 1;
     if (tail_vort) {  // omega of the first-layer ghosts needs the post-XSPH velocity of both layers
+      slab_bind(ctx, sb, xi++, n_ex);
       k = launch_slab_halo_pack(b.vel[1], sb, s);
       if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
       k += launch_slab_halo_unpack(b.vel[1], sb, s);
@@ -412,6 +612,10 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
   for (int attempt = 0; attempt < 16; ++attempt) {
     if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;
     if ((rc = ensure_tables(ctx)) != PBF_OK) return rc;
+    if ((rc = sl.transport->prepare(ctx, sl.msg_elems)) != PBF_OK) {  // last: may end in a barrier
+      sl.transport->abort();
+      return rc;
+    }
     if ((rc = reset_status(ctx)) != PBF_OK) return rc;
     if ((rc = set_device_count(ctx, (int)n0)) != PBF_OK) return rc;
     // Stream-ordered transports (NCCL) let the whole substep, exchanges included, replay as one
@@ -467,6 +671,13 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     if ((rc = sl.transport->reduce_status_host(ctx, &ctx->status_host->max_neighbors, kStatusShared)) != PBF_OK) return rc;
     const StatusBlock st = *ctx->status_host;
     ctx->last_status = st;
+    if (std::getenv("PBF_SLAB_DEBUG"))
+      std::fprintf(stderr, "[slab %d/%d] attempt %d nsteps %d: n_own %d->%d ghosts %d+%d b %d+%d send %d+%d | grid %u nbr %u mig %u ghost %u own %u far %u peer %u | max_send %u max_ghost %u max_own %u | mcap %d gcap %d cap %zu hops %d K %d\n",
+                   sl.rank, sl.nranks, attempt, nsteps, (int)n0, sl.counts_host->n_own, sl.counts_host->n_ghost[0],
+                   sl.counts_host->n_ghost[1], sl.counts_host->b[0], sl.counts_host->b[1], sl.counts_host->n_send[0],
+                   sl.counts_host->n_send[1], st.grid_overflow, st.nbr_overflow, st.mig_overflow, st.ghost_overflow,
+                   st.own_overflow, st.far_migrant, st.peer_failed, st.max_send, st.max_ghost, st.max_own, sl.mcap,
+                   sl.gcap, ctx->cap, sl.hops, ctx->K);
     const unsigned actionable = st.grid_overflow | st.nbr_overflow | st.mig_overflow | st.ghost_overflow |
                                 st.own_overflow | st.far_migrant;
     if (!actionable && st.peer_failed)
@@ -504,7 +715,10 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     if (st.nbr_overflow) ctx->K = (int)((st.max_neighbors + st.max_neighbors / 4 + 8 + 7u) & ~7u);
     if (st.mig_overflow) sl.mcap = (int)(st.max_send + st.max_send / 2 + 1024);
     if (st.ghost_overflow) sl.gcap = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
-    if (st.far_migrant) {
+    // far_migrant only counts when nothing else went wrong (a slab that stopped early leaves its
+    // neighbours with incomplete data, which can look like a stray particle)
+    const bool other = (st.grid_overflow | st.nbr_overflow | st.mig_overflow | st.ghost_overflow | st.own_overflow) != 0;
+    if (st.far_migrant && !other) {
       if (sl.hops >= std::max(1, sl.nranks - 1))
         return fail(ctx, PBF_E_COMM, "pbf_step: a particle is outside every reachable slab (non-finite position?)");
       sl.hops++;
@@ -590,6 +804,8 @@ int slab_enable(pbf_ctx* ctx, int rank, int nranks, Transport* tr, bool owns) {
 // ================================================================== C ABI
 extern "C" {
 
+int pbf_slab_set_p2p(pbf_ctx* ctx, int enabled);
+
 int pbf_slab_plan(size_t n, const float* px, float h, int nranks, int32_t* cuts) {
   if (!cuts || nranks < 1 || !(h > 0.0f) || (n > 0 && !px)) return fail(nullptr, PBF_E_INVALID, "pbf_slab_plan: bad arguments");
   std::vector<int> c;
@@ -625,7 +841,13 @@ int pbf_comm_init(pbf_ctx* ctx, int rank, int nranks, const void* id_bytes) {
     delete tr;
     return fail(ctx, PBF_E_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
   }
-  return slab_enable(ctx, rank, nranks, tr, true);
+  const int rc = slab_enable(ctx, rank, nranks, tr, true);
+  if (rc != PBF_OK) return rc;
+  // Default between processes: direct peer stores + flags (NCCL then only carries the IPC handles
+  // and the status agreement).  PBF_SLAB_P2P=0 keeps ncclSend/ncclRecv on the substep path.
+  const char* e = std::getenv("PBF_SLAB_P2P");
+  if (nranks > 1 && !(e && e[0] == '0')) return pbf_slab_set_p2p(ctx, 1);
+  return PBF_OK;
 }
 
 int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float* py, const float* pz,
@@ -670,6 +892,33 @@ int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, cons
 }
 
 size_t pbf_slab_owned(const pbf_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+int pbf_slab_set_p2p(pbf_ctx* ctx, int enabled) {
+  if (!ctx || !ctx->slab.enabled || !ctx->slab.transport) return fail(ctx, PBF_E_INVALID, "pbf_slab_set_p2p: not a slab context");
+  SlabState& sl = ctx->slab;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  PeerTransport* peer = dynamic_cast<PeerTransport*>(sl.transport);
+  if (enabled && !peer) {
+    PeerTransport* pt = new PeerTransport();
+    pt->inner = sl.transport;
+    pt->nccl = dynamic_cast<NcclTransport*>(sl.transport);
+    if (LocalTransport* lt = dynamic_cast<LocalTransport*>(sl.transport)) pt->group = lt->group;
+    if (!pt->nccl && !pt->group) {
+      pt->inner = nullptr;
+      delete pt;
+      return fail(ctx, PBF_E_INVALID, "pbf_slab_set_p2p: unknown transport");
+    }
+    sl.transport = pt;
+  } else if (!enabled && peer) {
+    sl.transport = peer->inner;
+    peer->inner = nullptr;
+    delete peer;
+  }
+  sl.warm = false;
+  invalidate_graph(ctx);
+  return PBF_OK;
+}
 
 int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi) {
   if (!ctx || !ctx->slab.enabled) return PBF_E_INVALID;
@@ -722,6 +971,7 @@ pbf_group* pbf_group_create(pbf_ctx** ctxs, int n) {
   g->send_ptr[0].assign((size_t)n, nullptr);
   g->send_ptr[1].assign((size_t)n, nullptr);
   g->words.resize((size_t)n);
+  g->window.assign((size_t)n, nullptr);
   for (int r = 0; r < n; ++r) {
     cudaSetDevice(ctxs[r]->device);
     cudaEventCreateWithFlags(&g->packed[(size_t)r], cudaEventDisableTiming);

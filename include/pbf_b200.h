@@ -203,6 +203,14 @@ int pbf_comm_unique_id(void* id_bytes);
 /* Joins the NCCL communicator of `nranks` slabs and turns ctx into slab `rank`.  Collective. */
 int pbf_comm_init(pbf_ctx* ctx, int rank, int nranks, const void* id_bytes);
 
+/* How halo data moves on the substep path.  1 = direct peer stores: the pack kernels write into
+ * the neighbour's memory (cudaIpc window between processes, plain pointers inside one process)
+ * and an exchange is one flag kernel — no message copy, no collective call; default after
+ * pbf_comm_init (environment PBF_SLAB_P2P=0 disables it).  0 = messages: ncclSend/ncclRecv
+ * between processes, peer copies inside a process (default for pbf_group_create).  Collective:
+ * every rank must choose the same mode before the next pbf_step. */
+int pbf_slab_set_p2p(pbf_ctx* ctx, int enabled);
+
 /* Distributes a global particle set: every rank passes the SAME global arrays (after
  * pbf_set_params) and keeps the particles of its slab; global ids = indices into these arrays. */
 int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float* py,

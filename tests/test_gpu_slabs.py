@@ -57,6 +57,44 @@ def test_virtual_slabs_bit_exact(built, nslabs, flags):
     grp.close()
 
 
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_virtual_slabs_direct_peer_stores(built, nslabs):
+    """The fused transport: pack kernels store straight into the neighbour's window and an exchange
+    is one flag kernel (pbf_slab_set_p2p).  Same bits as one GPU, stepping one substep at a time
+    (plain launches) and in batches (CUDA-graph replay with the flag kernels inside)."""
+    for flags, batches in ((H.STABLE_FLAGS, 3), (H.ALL_FLAGS, 1)):   # with vorticity the reference blows up soon
+        params, planes, state = _scene(scenes.SCENES["fluid_large"], flags, vx=1.5)
+        sol = _single(params, planes, state)
+        grp = SlabGroup([0] * nslabs, params, planes, p2p=True)
+        grp.upload(state)
+        for step in range(1, 4):
+            grp.step(1)
+            sol.step(1)
+            _assert_same(grp, sol, f"p2p step {step}")
+        for _ in range(batches):
+            grp.step(5)
+            sol.step(5)
+            _assert_same(grp, sol, "p2p batch of 5")
+        assert sum(grp.owned()) == len(state[0])
+        grp.close()
+
+
+def test_virtual_slabs_direct_peer_stores_growth(built):
+    """Capacity growth re-allocates the peer windows on every slab at once."""
+    params, planes, state = _scene(scenes.SCENES["fluid_large"], H.STABLE_FLAGS)
+    sol = _single(params, planes, state)
+    grp = SlabGroup([0] * 3, params, planes, p2p=True)
+    for s in grp.slabs:
+        s.lib.pbf_debug_set_slab_capacity.restype = C.c_int
+        s.lib.pbf_debug_set_slab_capacity.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        assert s.lib.pbf_debug_set_slab_capacity(s.ctx, 4, 64) == 0
+    grp.upload(state)
+    grp.step(3)
+    sol.step(3)
+    _assert_same(grp, sol, "p2p after growth")
+    grp.close()
+
+
 def test_virtual_slabs_migration(built):
     """The block drifts in +x at 3 m/s (a quarter cell per substep): particles cross the cuts all
     the time, pile up on the +x wall, and owned counts change."""
