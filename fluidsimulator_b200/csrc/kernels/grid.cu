@@ -78,19 +78,34 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
     lo[2] = min(lo[2], cz); hi[2] = max(hi[2], cz);
   }
   if (!do_bounds) return;  // slab mode: the bounds are taken after migration (k_slab_merge)
+  // block-level reduction first: six pre-checked atomics per BLOCK.  (Per-warp atomics made every
+  // warp poll the same L2 line; with one particle per thread that serialised the whole kernel.)
+  __shared__ int s_lo[3][kThreads / 32], s_hi[3][kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int wlo = __reduce_min_sync(0xffffffffu, lo[a]);
     const int whi = __reduce_max_sync(0xffffffffu, hi[a]);
-    if ((threadIdx.x & 31) == 0) {
-      // plain loads first: after the first few warps almost nobody needs the atomic
-      if (wlo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], wlo);
-      if (whi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], whi);
+    if (lane == 0) {
+      s_lo[a][warp] = wlo;
+      s_hi[a][warp] = whi;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    int blo = INT_MAX, bhi = INT_MIN;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      blo = min(blo, s_lo[a][w]);
+      bhi = max(bhi, s_hi[a][w]);
+    }
+    // plain loads first: after the first few blocks almost nobody needs the atomic
+    if (blo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], blo);
+    if (bhi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], bhi);
   }
 }
 
-// One thread: bounds -> GridDesc, capacity check, reset of the running bounds.
 // `pad` empty layers surround the occupied cells: 1 so the 27-cell stencil of every particle stays
 // inside the table; 2 in slab mode, where first-layer ghosts run their own stencil.
 __global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad) {
@@ -428,8 +443,6 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
   }
 }
 
-__global__ void k_begin_substep(StatusBlock* st) { st->total_neighbors = 0; }
-
 inline int grid_for(int n, int threads) { return (n + threads - 1) / threads; }
 
 }  // namespace
@@ -451,13 +464,14 @@ int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const s
 
 int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConsts& c,
                    const GridBuffers& g, NRef n, bool slab, cudaStream_t s) {
+  // one particle per thread up to 16 waves of 148 SMs x 8 blocks: enough loads in flight to
+  // stream at HBM speed, few enough warps that the six bound atomics stay cheap
   int blocks = grid_for(n.n, kThreads);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_begin_substep<<<1, 1, 0, s>>>(g.status);
+  if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
   k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n, slab ? 0 : 1);
-  if (slab) return 2;  // bounds + table descriptor follow the migration (launch_grid_finalize)
+  if (slab) return 1;  // bounds + table descriptor follow the migration (launch_grid_finalize)
   k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap, 1);
-  return 3;
+  return 2;
 }
 
 int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s) {

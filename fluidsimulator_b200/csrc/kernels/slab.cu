@@ -228,14 +228,29 @@ k_slab_merge(const float4* __restrict__ keep_pos, const float4* __restrict__ kee
     }
   }
   if (!last_hop) return;
+  // block-level reduction, then six pre-checked atomics per block (see k_predict)
+  __shared__ int s_lo[3][kThreads / 32], s_hi[3][kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int wlo = __reduce_min_sync(0xffffffffu, lo[a]);
     const int whi = __reduce_max_sync(0xffffffffu, hi[a]);
-    if ((threadIdx.x & 31) == 0) {
-      if (wlo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], wlo);
-      if (whi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], whi);
+    if (lane == 0) {
+      s_lo[a][warp] = wlo;
+      s_hi[a][warp] = whi;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    int blo = INT_MAX, bhi = INT_MIN;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      blo = min(blo, s_lo[a][w]);
+      bhi = max(bhi, s_hi[a][w]);
+    }
+    if (blo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], blo);
+    if (bhi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], bhi);
   }
 }
 
