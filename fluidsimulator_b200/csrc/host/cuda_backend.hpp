@@ -2,6 +2,8 @@
 // backend (reference cuda/include/fluid/cuda.h:7-9), re-created on top of the C ABI.
 #pragma once
 
+#include <vector>
+
 #ifdef PBF_USE_REFERENCE_HEADERS
 #include "fluid/core.h"   // the reference's own header (drop-in build)
 #else
@@ -19,7 +21,8 @@ void cuda_step(const Params& params, State& state);           // cuda.h:9
 namespace b200 {
 struct Options {
   int device = 0;
-  bool fast_mode = false;  // PBF_MODE_FAST instead of the bit-exact default
+  std::vector<int> devices;  // more than one entry: x-slabs over these devices (pbf_group_*)
+  bool fast_mode = false;    // PBF_MODE_FAST instead of the bit-exact default
 };
 void configure(const Options& options);            // before the first step
 void upload(const Params& params, const State& state);

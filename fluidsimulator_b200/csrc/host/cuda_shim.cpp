@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "pbf_b200.h"
 
@@ -20,7 +21,9 @@ namespace fluid {
 namespace {
 
 struct Backend {
-  pbf_ctx* ctx = nullptr;
+  pbf_ctx* ctx = nullptr;            // the only context, or slab 0 of the group
+  std::vector<pbf_ctx*> slabs;       // --devices: one context per device ...
+  pbf_group* group = nullptr;        // ... linked as x-slabs
   b200::Options options;
   pbf_params last_params{};
   bool params_valid = false;
@@ -44,11 +47,39 @@ void check(int rc, const char* what) {
 pbf_ctx* context(std::size_t capacity) {
   Backend& b = backend();
   if (!b.ctx) {
-    b.ctx = pbf_create(b.options.device, capacity);
-    if (!b.ctx) die("pbf_create", nullptr);
-    check(pbf_set_mode(b.ctx, b.options.fast_mode ? PBF_MODE_FAST : PBF_MODE_STRICT), "pbf_set_mode");
+    const int mode = b.options.fast_mode ? PBF_MODE_FAST : PBF_MODE_STRICT;
+    if (b.options.devices.size() > 1) {
+      for (int dev : b.options.devices) {
+        pbf_ctx* c = pbf_create(dev, 0);
+        if (!c) die("pbf_create", nullptr);
+        if (pbf_set_mode(c, mode) != PBF_OK) die("pbf_set_mode", c);
+        b.slabs.push_back(c);
+      }
+      b.group = pbf_group_create(b.slabs.data(), static_cast<int>(b.slabs.size()));
+      if (!b.group) die("pbf_group_create", nullptr);
+      b.ctx = b.slabs[0];
+    } else {
+      b.ctx = pbf_create(b.options.device, capacity);
+      if (!b.ctx) die("pbf_create", nullptr);
+      check(pbf_set_mode(b.ctx, mode), "pbf_set_mode");
+    }
   }
   return b.ctx;
+}
+
+// every context of the backend (one, or all slabs)
+std::vector<pbf_ctx*> all_contexts() {
+  Backend& b = backend();
+  return b.slabs.empty() ? std::vector<pbf_ctx*>{b.ctx} : b.slabs;
+}
+
+void check_slabs(int rc, const char* what) {
+  if (rc == PBF_OK) return;
+  for (pbf_ctx* c : all_contexts()) {
+    const char* msg = pbf_last_error(c);
+    if (msg && msg[0]) die(what, c);
+  }
+  die(what, backend().ctx);
 }
 
 pbf_params to_pod(const Params& p) {
@@ -91,16 +122,19 @@ void sync_params(const Params& params, std::size_t capacity) {
   planes.insert(planes.end(), params.planes.ny.begin(), params.planes.ny.end());
   planes.insert(planes.end(), params.planes.nz.begin(), params.planes.nz.end());
   planes.insert(planes.end(), params.planes.d.begin(), params.planes.d.end());
+  (void)ctx;
   if (!b.params_valid || planes != b.plane_cache) {
-    check(pbf_set_planes(ctx, static_cast<int>(np), planes.data(), planes.data() + np, planes.data() + 2 * np,
-                         planes.data() + 3 * np),
-          "pbf_set_planes");
+    for (pbf_ctx* c : all_contexts())
+      if (pbf_set_planes(c, static_cast<int>(np), planes.data(), planes.data() + np, planes.data() + 2 * np,
+                         planes.data() + 3 * np) != PBF_OK)
+        die("pbf_set_planes", c);
     b.plane_cache = planes;
     b.params_valid = false;
   }
   const pbf_params pod = to_pod(params);
   if (!b.params_valid || std::memcmp(&pod, &b.last_params, sizeof(pod)) != 0) {
-    check(pbf_set_params(ctx, &pod), "pbf_set_params");
+    for (pbf_ctx* c : all_contexts())
+      if (pbf_set_params(c, &pod) != PBF_OK) die("pbf_set_params", c);
     b.last_params = pod;
     b.params_valid = true;
   }
@@ -144,31 +178,52 @@ void configure(const Options& options) { backend().options = options; }
 
 void upload(const Params& params, const State& state) {
   sync_params(params, state.size());
-  pbf_ctx* ctx = backend().ctx;
-  check(pbf_upload(ctx, state.size(), state.pos_x.data(), state.pos_y.data(), state.pos_z.data(),
-                   state.vel_x.data(), state.vel_y.data(), state.vel_z.data()),
-        "pbf_upload");
-  check(pbf_set_time(ctx, state.time), "pbf_set_time");
+  Backend& b = backend();
+  if (b.group) {
+    check_slabs(pbf_group_upload(b.group, state.size(), state.pos_x.data(), state.pos_y.data(), state.pos_z.data(),
+                                 state.vel_x.data(), state.vel_y.data(), state.vel_z.data()),
+                "pbf_group_upload");
+  } else {
+    check(pbf_upload(b.ctx, state.size(), state.pos_x.data(), state.pos_y.data(), state.pos_z.data(),
+                     state.vel_x.data(), state.vel_y.data(), state.vel_z.data()),
+          "pbf_upload");
+  }
+  for (pbf_ctx* c : all_contexts())
+    if (pbf_set_time(c, state.time) != PBF_OK) die("pbf_set_time", c);
 }
 
 void step_resident(const Params& params, int nsteps) {
-  sync_params(params, pbf_count(backend().ctx));
-  check(pbf_step(backend().ctx, nsteps), "pbf_step");
+  Backend& b = backend();
+  sync_params(params, pbf_count(b.ctx));
+  if (b.group)
+    check_slabs(pbf_group_step(b.group, nsteps), "pbf_group_step");
+  else
+    check(pbf_step(b.ctx, nsteps), "pbf_step");
 }
 
 void download_positions(State& state) {
-  pbf_ctx* ctx = backend().ctx;
-  check(pbf_download(ctx, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), nullptr, nullptr, nullptr),
-        "pbf_download");
-  state.time = pbf_time(ctx);
+  Backend& b = backend();
+  if (b.group)
+    check_slabs(pbf_group_download(b.group, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), nullptr,
+                                   nullptr, nullptr),
+                "pbf_group_download");
+  else
+    check(pbf_download(b.ctx, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), nullptr, nullptr, nullptr),
+          "pbf_download");
+  state.time = pbf_time(b.ctx);
 }
 
 void download(State& state) {
-  pbf_ctx* ctx = backend().ctx;
-  check(pbf_download(ctx, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), state.vel_x.data(),
-                     state.vel_y.data(), state.vel_z.data()),
-        "pbf_download");
-  state.time = pbf_time(ctx);
+  Backend& b = backend();
+  if (b.group)
+    check_slabs(pbf_group_download(b.group, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(),
+                                   state.vel_x.data(), state.vel_y.data(), state.vel_z.data()),
+                "pbf_group_download");
+  else
+    check(pbf_download(b.ctx, state.pos_x.data(), state.pos_y.data(), state.pos_z.data(), state.vel_x.data(),
+                       state.vel_y.data(), state.vel_z.data()),
+          "pbf_download");
+  state.time = pbf_time(b.ctx);
 }
 
 float device_time() { return pbf_time(backend().ctx); }
@@ -176,7 +231,14 @@ void set_device_time(float t) { check(pbf_set_time(backend().ctx, t), "pbf_set_t
 
 void shutdown() {
   Backend& b = backend();
-  if (b.ctx) pbf_destroy(b.ctx);
+  if (b.group) {
+    pbf_group_destroy(b.group);  // before its contexts
+    b.group = nullptr;
+    for (pbf_ctx* c : b.slabs) pbf_destroy(c);
+    b.slabs.clear();
+  } else if (b.ctx) {
+    pbf_destroy(b.ctx);
+  }
   b.ctx = nullptr;
   b.params_valid = false;
 }

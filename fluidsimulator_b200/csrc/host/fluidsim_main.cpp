@@ -7,15 +7,26 @@
 //   --device N              CUDA device index.
 //   --per-step-host         use the reference's cuda_step contract (host round trip per step)
 //                           instead of device-resident stepping.
+//   --devices 0,1,2,3       split the scene into x-slabs over several GPUs of this process
+//                           (halo exchange by peer copies; results identical to one GPU).
+// Device-resident runs execute all substeps up to the next output step as ONE batch (no host
+// synchronisation in between), and frames are rendered and written by a background thread while
+// the GPU already computes the next batch (row f1 of SURVEY §8: the ASCII writer costs ~78 bytes
+// per particle and dominated the wall time of a run with output).
 // The state stays on the GPU between steps; positions come back only on output steps
 // (main.cpp:259-273 reads state.pos_* only there).  --backend=cpu is refused: this product
 // has no CPU fallback (the reference's own binary provides it).
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
 #include <iostream>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cuda_backend.hpp"
@@ -35,6 +46,85 @@ bool parse_double(const fluid::b200::ParsedOptions& parsed, const char* name, do
     return false;
   }
   return true;
+}
+
+// Frames are handed to one writer thread; at most two are in flight, so a slow disk throttles
+// the simulation instead of exhausting memory.
+struct FrameJob {
+  std::vector<float> x, y, z;
+  double time = 0.0;
+  std::size_t index = 0;
+};
+
+class AsyncFrames {
+ public:
+  explicit AsyncFrames(const fluid::b200::FrameWriter& writer) : writer_(writer), thread_([this] { run(); }) {}
+  ~AsyncFrames() { finish(); }
+  void submit(std::unique_ptr<FrameJob> job) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return queue_.size() < 2; });
+    queue_.push_back(std::move(job));
+    cv_.notify_all();
+  }
+  bool finish() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (done_) return ok_;
+      done_ = true;
+      cv_.notify_all();
+    }
+    thread_.join();
+    return ok_;
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      std::unique_ptr<FrameJob> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !queue_.empty() || done_; });
+        if (queue_.empty()) return;
+        job = std::move(queue_.front());
+        queue_.pop_front();
+        cv_.notify_all();
+      }
+      fluid::b200::FrameView view;
+      view.pos_x = job->x.data();
+      view.pos_y = job->y.data();
+      view.pos_z = job->z.data();
+      view.count = job->x.size();
+      view.time = job->time;
+      if (!writer_.write(view, job->index)) ok_ = false;
+    }
+  }
+  const fluid::b200::FrameWriter& writer_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::unique_ptr<FrameJob>> queue_;
+  bool done_ = false;
+  bool ok_ = true;
+  std::thread thread_;
+};
+
+bool parse_devices(const std::string& text, std::vector<int>& out) {
+  out.clear();
+  std::size_t pos = 0;
+  while (pos <= text.size()) {
+    const std::size_t comma = text.find(',', pos);
+    const std::string item = text.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+    try {
+      std::size_t used = 0;
+      const int d = std::stoi(item, &used);
+      if (used != item.size() || d < 0) return false;
+      out.push_back(d);
+    } catch (const std::exception&) {
+      return false;
+    }
+    if (comma == std::string::npos) break;
+    pos = comma + 1;
+  }
+  return !out.empty();
 }
 
 }  // namespace
@@ -61,6 +151,7 @@ int main(int argc, char** argv) {
       {"mode", true, "Arithmetic mode: strict (bit-identical to the CPU path, default) or fast."},
       {"device", true, "CUDA device index (default 0)."},
       {"per-step-host", false, "Round-trip the state through host memory every step (cuda_step contract)."},
+      {"devices", true, "Comma-separated CUDA devices: split the scene into x-slabs over them (e.g. 0,1,2,3)."},
   };
   const fluid::b200::ParsedOptions parsed = fluid::b200::parse_options(argc, argv, options);
   if (!parsed.ok) {
@@ -160,6 +251,18 @@ int main(int argc, char** argv) {
       return 1;
     }
   }
+  std::vector<int> devices;
+  if (parsed.has("devices")) {
+    if (!parse_devices(parsed.value("devices", ""), devices)) {
+      std::cerr << "Invalid devices value (expected e.g. 0,1,2,3)." << std::endl;
+      return 1;
+    }
+    if (parsed.has("per-step-host")) {
+      std::cerr << "--devices and --per-step-host exclude each other." << std::endl;
+      return 1;
+    }
+    device = devices[0];
+  }
   const std::string mode = parsed.value("mode", "strict");
   if (mode != "strict" && mode != "fast") {
     std::cerr << "mode must be strict or fast." << std::endl;
@@ -225,37 +328,54 @@ int main(int argc, char** argv) {
 
   fluid::b200::Options backend_options;
   backend_options.device = device;
+  backend_options.devices = devices;
   backend_options.fast_mode = (mode == "fast");
   fluid::b200::configure(backend_options);
   const bool per_step_host = parsed.has("per-step-host");
-  if (!per_step_host && state.size() > 0) fluid::b200::upload(params, state);
+  const bool resident = !per_step_host && state.size() > 0;
+  if (resident) fluid::b200::upload(params, state);
+  if (devices.size() > 1) std::cout << "slabs=" << devices.size() << std::endl;
 
-  for (int step = 0; step < steps; ++step) {
+  AsyncFrames async_frames(frames);
+  int step = 0;
+  while (step < steps) {
     const auto t0 = std::chrono::steady_clock::now();
-    const bool wants_frame = output_enabled && (step % output_interval == 0);
-    if (per_step_host || state.size() == 0) {
+    // steps [step, last] run as one batch; `last` is the next step after which a frame is due
+    int last = step;
+    if (resident && !debug_print) {
+      last = steps - 1;
+      if (output_enabled) {
+        const int next_frame = ((step + output_interval - 1) / output_interval) * output_interval;
+        last = std::min(last, next_frame);
+      }
+    }
+    const int batch = last - step + 1;
+    const bool wants_frame = output_enabled && (last % output_interval == 0);
+    if (!resident) {
       fluid::cuda_step(params, state);
     } else {
-      fluid::b200::step_resident(params, 1);
+      fluid::b200::step_resident(params, batch);
       if (wants_frame) fluid::b200::download_positions(state);
     }
+    step = last + 1;
     const auto t1 = std::chrono::steady_clock::now();
-    const double step_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    const double step_ms = std::chrono::duration<double, std::milli>(t1 - t0).count() / batch;
     if (wants_frame) {
-      fluid::b200::FrameView view;
-      view.pos_x = state.pos_x.data();
-      view.pos_y = state.pos_y.data();
-      view.pos_z = state.pos_z.data();
-      view.count = state.size();
-      view.time = state.time;
-      if (!frames.write(view, frame_index)) {
-        std::cerr << "Failed to write VTK frame." << std::endl;
-        return 1;
-      }
+      std::unique_ptr<FrameJob> job(new FrameJob());
+      job->x = state.pos_x;
+      job->y = state.pos_y;
+      job->z = state.pos_z;
+      job->time = state.time;
+      job->index = frame_index;
+      async_frames.submit(std::move(job));
       series.add(state.time, fluid::b200::frame_filename("frame", frame_index));
       frame_index++;
     }
-    if (debug_print) std::cout << "step_done=" << (step + 1) << " step_ms=" << step_ms << std::endl;
+    if (debug_print) std::cout << "step_done=" << step << " step_ms=" << step_ms << std::endl;
+  }
+  if (!async_frames.finish()) {
+    std::cerr << "Failed to write VTK frame." << std::endl;
+    return 1;
   }
   if (!per_step_host && state.size() > 0) fluid::b200::download(state);
   std::cout << "particle_count=" << state.size() << std::endl;

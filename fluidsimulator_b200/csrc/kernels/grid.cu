@@ -401,7 +401,7 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
   if (active) {
     uint32_t* out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
     const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
-    const f2 xi = bcast(pi.x), yi = bcast(pi.y), zi = bcast(pi.z);
+    const f2 pxy = make_float2(pi.x, pi.y);
     for (int dz = -1; dz <= 1; ++dz)
       for (int dy = -1; dy <= 1; ++dy) {
         const uint32_t row = ((uint32_t)(cx - 1) * (uint32_t)dimy + (uint32_t)(cy + dy)) * (uint32_t)dimz +
@@ -416,12 +416,14 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
             const int j1 = v1 ? j + 1 : j;
             const float4 a0 = pred_s[j];
             const float4 a1 = pred_s[j1];
-            const f2 ddx = __fadd2_rn(xi, make_float2(-a0.x, -a1.x));
-            const f2 ddy = __fadd2_rn(yi, make_float2(-a0.y, -a1.y));
-            const f2 ddz = __fadd2_rn(zi, make_float2(-a0.z, -a1.z));
-            const f2 sx = __fmul2_rn(ddx, ddx), sy = __fmul2_rn(ddy, ddy), sz = __fmul2_rn(ddz, ddz);
-            const float r2a = __fadd_rn(__fadd_rn(sx.x, sy.x), sz.x);
-            const float r2b = __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y);
+            // x and y of ONE candidate share an f32x2 (they sit in an aligned register pair after
+            // the 16-byte load: no packing moves), z is scalar; same roundings as (dx*dx + dy*dy) + dz*dz
+            const f2 d0 = __fadd2_rn(pxy, make_float2(-a0.x, -a0.y));
+            const f2 d1 = __fadd2_rn(pxy, make_float2(-a1.x, -a1.y));
+            const float z0 = __fsub_rn(pi.z, a0.z), z1 = __fsub_rn(pi.z, a1.z);
+            const f2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
+            const float r2a = __fadd_rn(__fadd_rn(q0.x, q0.y), __fmul_rn(z0, z0));
+            const float r2b = __fadd_rn(__fadd_rn(q1.x, q1.y), __fmul_rn(z1, z1));
             if (j != i && r2a < h2) {  // core.cpp:231-240
               if (cnt < (uint32_t)K) __stcs(out + (size_t)(cnt >> 1) * 64u + (cnt & 1u), (uint32_t)j);
               ++cnt;

@@ -64,3 +64,19 @@ def test_own_app_matches_reference_app(built, tmp_path):
 def test_own_app_default_scene_and_iterations(built, tmp_path):
     out = run(APP, "--steps", 3, "--no-output", "--solver-iterations", 2, "--debug-print")
     assert "particle_count=46875" in out and "step_done=3" in out and "output_enabled=false" in out
+
+
+def test_own_app_slabs_and_batched_output(built, tmp_path):
+    """`--devices 0,0,0`: three x-slabs (here on one GPU) driven by the application; batched
+    stepping between output frames and the background frame writer.  Files are byte-identical to
+    the single-context run, which the test above ties to the reference application."""
+    scene = scenes.SCENES["fluid_large"].write_json(tmp_path / "scene.json")
+    one, three = tmp_path / "one", tmp_path / "three"
+    stable = ["--steps-per-sec", "120", "--enable-scorr", "--enable-xsph", "--plane-restitution", "0.05",
+              "--plane-friction", "0.1"]
+    a = run(APP, "--scene", scene, "--steps", 14, "--fps", 30, "--output-dir", one, *stable)
+    b = run(APP, "--scene", scene, "--steps", 14, "--fps", 30, "--output-dir", three, "--devices", "0,0,0", *stable)
+    names = same_tree(one, three)
+    assert len(names) == 5 and "slabs=3" in b     # frames after steps 1, 5, 9, 13 + series.pvd
+    pick = lambda s: [l for l in s.splitlines() if l.split("=")[0] in ("particle_count", "end_time")]
+    assert pick(a) == pick(b)
