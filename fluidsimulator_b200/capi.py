@@ -161,6 +161,7 @@ ABI = {
     "pbf_slab_set_p2p": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
     "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
+    "pbf_slab_set_cuts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "pbf_slab_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32p, _i32p]),
     "pbf_group_create": (C.c_void_p, [C.POINTER(C.c_void_p), C.c_int]),
     "pbf_group_destroy": (None, [C.c_void_p]),
@@ -386,6 +387,9 @@ class SlabSolver(Solver):
         self._check(self.lib.pbf_slab_cuts(self.ctx, iptr(lo), iptr(hi)))
         return int(lo[0]), int(hi[0])
 
+    def set_cuts(self, lo: int, hi: int):
+        self._check(self.lib.pbf_slab_set_cuts(self.ctx, int(lo), int(hi)))
+
     def slab_download(self, out=None):
         """(global ids, six SoA arrays) of the owned particles.  `out` = (int64 array, six float32
         arrays) of sufficient capacity (e.g. pinned) to receive them in place."""
@@ -446,6 +450,14 @@ class SlabGroup:
 
     def owned(self):
         return [s.owned() for s in self.slabs]
+
+    def rebalance(self, h: float):
+        """New equal-count cuts from the current positions (pbf_slab_plan) on every slab."""
+        px = self.download()[0]
+        cuts = slab_plan(px, h, len(self.slabs))
+        for r, s in enumerate(self.slabs):
+            s.set_cuts(cuts[r], cuts[r + 1])
+        return cuts
 
     def close(self):
         if getattr(self, "group", None):

@@ -66,6 +66,7 @@ struct SolveBuffers {
   float4* vel_o;
   StatusBlock* status;
   DebugPtrs dbg;
+  HaloOut halo;      // slab mode: where the next delta / xsph launch also stores its boundary layers
 };
 
 // a8..a14 for one substep: I x (lambda, delta), velocity update, XSPH, vorticity,
@@ -119,8 +120,8 @@ int launch_slab_ghost_pack(const uint32_t* keys_sorted, const float4* pred_s, co
 // append received ghosts after the owned slots and insert their cells into the table
 int launch_slab_ghost_unpack(float4* pred_s, float4* pos_s, const GridBuffers& g, const SlabBuffers& sb,
                              const StepConsts& c, cudaStream_t s);
-// per-iteration refresh of one float4 array: boundary slots -> messages, messages -> ghost slots
-int launch_slab_halo_pack(const float4* arr, const SlabBuffers& sb, cudaStream_t s);
+// per-iteration refresh of one float4 array: messages -> ghost slots (the boundary slots are stored
+// into the messages by the producing delta / xsph launch, SolveBuffers::halo)
 int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s);
 // ghost velocities (pred - pos)/dt and m/rho, recomputed locally after the last pred refresh
 int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel,

@@ -364,17 +364,7 @@ k_slab_ghost_unpack(const float4* __restrict__ recv_l, const float4* __restrict_
 }
 
 // ---------------------------------------------------------------- per-iteration halo refresh
-__global__ void __launch_bounds__(kThreads)
-k_slab_halo_pack(const float4* __restrict__ arr, const SlabCounts* __restrict__ counts, float4* __restrict__ send_l,
-                 float4* __restrict__ send_r, const StatusBlock* st, int gcap) {
-  if (batch_failed(st)) return;
-  const int t = blockIdx.x * kThreads + threadIdx.x;
-  const int side = t / gcap, k = t - side * gcap;
-  if (side > 1 || k >= counts->b[side]) return;
-  const int src = side == 0 ? k : counts->n_own - counts->b[1] + k;
-  (side == 0 ? send_l : send_r)[k] = arr[src];
-}
-
+// (the outgoing side is HaloOut::put inside the delta / xsph kernels, kernels/solve.cu)
 __global__ void __launch_bounds__(kThreads)
 k_slab_halo_unpack(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ arr,
                    const SlabCounts* __restrict__ counts, const StatusBlock* st, int gcap) {
@@ -450,12 +440,6 @@ int launch_slab_ghost_unpack(float4* pred_s, float4* pos_s, const GridBuffers& g
   k_slab_ghost_unpack<<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(sb.recv[0], sb.recv[1], pred_s, pos_s, g.cell_range,
                                                                 g.desc, sb.counts, sb.status, c.inv_h, sb.gcap,
                                                                 sb.tot_cap);
-  return 1;
-}
-
-int launch_slab_halo_pack(const float4* arr, const SlabBuffers& sb, cudaStream_t s) {
-  k_slab_halo_pack<<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(arr, sb.counts, sb.send[0], sb.send[1], sb.status,
-                                                             sb.gcap);
   return 1;
 }
 

@@ -353,7 +353,7 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
         const float4* __restrict__ pos_s, const float* __restrict__ rho, float4* __restrict__ vel_out,
         const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
-        StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final, int K, NRef nr) {
+        StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final, int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
@@ -413,6 +413,7 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
   const F nx_ = xi + ax, ny_ = yi + ay, nz_ = zi + az;
   const float4 np = make_float4(Arith<F>::val(nx_), Arith<F>::val(ny_), Arith<F>::val(nz_), 0.0f);
   pred_out[i] = np;
+  halo.put(i, np);
   if (LAST) {  // core.cpp:414-420
     const float4 p0 = pos_s[i];
     V3<F> v;
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4* __restrict__ vel_out,
        const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
        const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
-       float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, int is_final,
+       float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final,
        int K, NRef nr) {
   using M = M2<S>;
   using F = FT<S>;
@@ -472,7 +473,9 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
   if (is_final) {
     finalize_particle<F>(pi, v, __float_as_uint(pos_s[i].w), c, planes, pos_o, vel_o);
   } else {
-    vel_out[i] = make_float4(Arith<F>::val(v.x), Arith<F>::val(v.y), Arith<F>::val(v.z), vi.w);
+    const float4 vo = make_float4(Arith<F>::val(v.x), Arith<F>::val(v.y), Arith<F>::val(v.z), vi.w);
+    vel_out[i] = vo;
+    halo.put(i, vo);
   }
 }
 
@@ -619,11 +622,11 @@ static void delta_impl(const SolveBuffers& b, const NeighborList& nl, const Step
                        bool is_final, NRef n, cudaStream_t s) {
   if (last)
     k_delta<S, true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                     b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg,
+                                                     b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo,
                                                      is_final ? 1 : 0, nl.K, n);
   else
     k_delta<S, false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                      b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, 0,
+                                                      b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo, 0,
                                                       nl.K, n);
 }
 
@@ -638,10 +641,10 @@ int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts&
                 NRef n, bool strict, cudaStream_t s) {
   if (strict)
     k_xsph<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
-                                                 b.vel_o, c, b.status, b.dbg, is_final ? 1 : 0, nl.K, n);
+                                                 b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   else
     k_xsph<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
-                                                  b.vel_o, c, b.status, b.dbg, is_final ? 1 : 0, nl.K, n);
+                                                  b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   return 1;
 }
 

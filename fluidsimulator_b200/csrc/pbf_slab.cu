@@ -523,15 +523,23 @@ int slab_substep(pbf_ctx* ctx) {
     stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
     launches += launch_lambda(b, nl, c, cur, n_tot, strict, s);  // owned + first-layer ghosts
     stage_mark(ctx, PBF_STAGE_LAMBDA, 0);
+    // the delta pass stores its two boundary layers straight into the outgoing messages (no pack
+    // kernel); after the very last pass nothing reads the ghosts any more
+    const bool refresh = !(last && final_in_delta);
+    b.halo = HaloOut{nullptr, {nullptr, nullptr}};
+    if (refresh) {
+      slab_bind(ctx, sb, xi++, n_ex);
+      b.halo = HaloOut{sb.counts, {sb.send[0], sb.send[1]}};
+    }
     stage_mark(ctx, PBF_STAGE_DELTA, 1);
     launches += launch_delta(b, nl, c, cur, last, last && final_in_delta, n_own, strict, s);
     stage_mark(ctx, PBF_STAGE_DELTA, 0);
+    b.halo = HaloOut{nullptr, {nullptr, nullptr}};
     t.launches[PBF_STAGE_LAMBDA] += 1;
     t.launches[PBF_STAGE_DELTA] += 1;
     cur ^= 1;
-    if (last && final_in_delta) break;  // nothing reads the ghosts any more
-    slab_bind(ctx, sb, xi++, n_ex);
-    k = launch_slab_halo_pack(b.pred[cur], sb, s);
+    if (!refresh) break;
+    k = 0;
     if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
     k += launch_slab_halo_unpack(b.pred[cur], sb, s);
     t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
@@ -543,14 +551,18 @@ int slab_substep(pbf_ctx* ctx) {
   t.launches[PBF_STAGE_EXCHANGE] += 1;
   int vcur = 0;
   if (tail_xsph) {
+    if (tail_vort) {  // omega of the first-layer ghosts needs the post-XSPH velocity of both layers
+      slab_bind(ctx, sb, xi++, n_ex);
+      b.halo = HaloOut{sb.counts, {sb.send[0], sb.send[1]}};
+    }
     stage_mark(ctx, PBF_STAGE_XSPH, 1);
     launches += launch_xsph(b, nl, c, pos, !tail_vort, n_own, strict, s);
     stage_mark(ctx, PBF_STAGE_XSPH, 0);
+    b.halo = HaloOut{nullptr, {nullptr, nullptr}};
     t.launches[PBF_STAGE_XSPH] += 1;
     vcur = 1;
-    if (tail_vort) {  // omega of the first-layer ghosts needs the post-XSPH velocity of both layers
-      slab_bind(ctx, sb, xi++, n_ex);
-      k = launch_slab_halo_pack(b.vel[1], sb, s);
+    if (tail_vort) {
+      k = 0;
       if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
       k += launch_slab_halo_unpack(b.vel[1], sb, s);
       t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
@@ -917,6 +929,18 @@ int pbf_slab_set_p2p(pbf_ctx* ctx, int enabled) {
   }
   sl.warm = false;
   invalidate_graph(ctx);
+  return PBF_OK;
+}
+
+int pbf_slab_set_cuts(pbf_ctx* ctx, int32_t lo, int32_t hi) {
+  if (!ctx || !ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_slab_set_cuts: not a slab context");
+  const bool first = ctx->slab.rank == 0, last = ctx->slab.rank == ctx->slab.nranks - 1;
+  if ((first && lo != INT_MIN) || (last && hi != INT_MAX) || (!first && lo == INT_MIN) || (!last && hi == INT_MAX) ||
+      (long long)hi - (long long)lo < 2)
+    return fail(ctx, PBF_E_INVALID, "pbf_slab_set_cuts: cuts must tile the x axis with >= 2 cell layers per slab");
+  ctx->slab.cut_lo = lo;
+  ctx->slab.cut_hi = hi;
+  invalidate_graph(ctx);  // the cuts are kernel parameters of the captured substep
   return PBF_OK;
 }
 

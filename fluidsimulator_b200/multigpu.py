@@ -70,6 +70,27 @@ def gather_global(dist, gid: np.ndarray, state6, n_global: int, device):
     return out
 
 
+def rebalance(dist, sol: SlabSolver, h: float, device) -> np.ndarray:
+    """Collective: gathers the x coordinates of every slab, plans equal-count cuts on them
+    (pbf_slab_plan — the same planner the upload uses) and installs them.  Misplaced particles
+    migrate during the next substep; results do not depend on the cuts."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    _, st = sol.slab_download()
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = st[0].shape[0]
+    dist.all_reduce(counts)
+    nmax = int(counts.max().item())
+    mine = torch.zeros(nmax, dtype=torch.float32, device=device)
+    mine[: st[0].shape[0]] = torch.from_numpy(st[0]).to(device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    px = np.concatenate([parts[r][: int(counts[r].item())].cpu().numpy() for r in range(world)])
+    cuts = slab_plan(px, h, world)
+    sol.set_cuts(cuts[rank], cuts[rank + 1])
+    return cuts
+
+
 # ---- GPU side ------------------------------------------------------------------------------------
 def make_slab(dist, local: int, params, planes, state, mode, stream_ptr=None) -> SlabSolver:
     import torch

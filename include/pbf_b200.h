@@ -224,6 +224,11 @@ int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, cons
  * owned particles with their global ids (ascending). */
 size_t pbf_slab_owned(const pbf_ctx* ctx);
 int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi);
+/* Re-balancing: new cuts for this slab (e.g. from pbf_slab_plan on the gathered positions).  By
+ * convention collective — the cuts of all ranks must tile the x axis.  Particles that now lie in
+ * another slab migrate during the next substep (one hop per slab of distance; the hop count
+ * grows on demand), so results do not depend on when or how the cuts move. */
+int pbf_slab_set_cuts(pbf_ctx* ctx, int32_t lo, int32_t hi);
 int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py,
                       float* pz, float* vx, float* vy, float* vz);
 /* Exchanges and bytes sent since creation, ghosts held after the last substep, migration hops. */

@@ -196,3 +196,23 @@ def test_nccl_slabs_two_gpus(built):
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "slab check ok" in out.stdout
+
+
+def test_virtual_slabs_rebalance(built):
+    """Cuts re-planned in the middle of a run (pbf_slab_set_cuts): whole cell layers change owner
+    during the next substep, several hops for some, message capacities grow — same bits as one GPU."""
+    params, planes, state = _scene(scenes.SCENES["fluid_large"], H.STABLE_FLAGS, vx=2.0)
+    sol = _single(params, planes, state)
+    grp = SlabGroup([0] * 4, params, planes)
+    grp.upload(state)
+    grp.step(20)
+    sol.step(20)
+    before = [s.cuts() for s in grp.slabs]
+    cuts = grp.rebalance(float(params.h))
+    assert [s.cuts() for s in grp.slabs] != before and len(cuts) == 5
+    grp.step(6)
+    sol.step(6)
+    _assert_same(grp, sol, "after rebalancing")
+    counts = grp.owned()
+    assert max(counts) - min(counts) < 0.2 * sum(counts)
+    grp.close()
