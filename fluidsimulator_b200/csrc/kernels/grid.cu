@@ -25,6 +25,9 @@ namespace pbf {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef PBF_COUNTING_SORT
+#define PBF_COUNTING_SORT 1
+#endif
 // ---------------------------------------------------------------- state (de)interleave
 __global__ void __launch_bounds__(kThreads)
 k_pack_state(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
@@ -338,6 +341,120 @@ k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
   }
 }
 
+// ---------------------------------------------------------------- a5 + a6 as a counting sort
+// The key is a dense cell index, so the sort of core.cpp:173-183 plus the run-length table of
+// core.cpp:185-203 is a counting sort: count per cell, exclusive scan = cell starts (= the table),
+// place.  The reference order inside a cell is ascending particle id (core.cpp:182); atomics hand
+// out arrival slots in arbitrary order, so the last kernel ranks every particle among the (few)
+// members of its cell by id — O(occupancy) reads per particle — and writes the final slot together
+// with the gathered positions.  6 launches instead of 14 for the 3-pass radix sort + table, and the
+// result is bit-identical to it (kept below as the reference implementation, PBF_COUNTING_SORT=0).
+__global__ void __launch_bounds__(kThreads)
+k_cell_count(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ arrival,
+             uint32_t* __restrict__ cell_count, float inv_h, const GridDesc* __restrict__ desc,
+             const StatusBlock* st, NRef nr) {
+  if (batch_failed(st)) return;
+  const int n = nr.get();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = dense_key(pred_o[i], inv_h, *desc);
+  keys[i] = k;
+  arrival[i] = atomicAdd(&cell_count[k], 1u);
+}
+
+// chunk-local exclusive scan of the cell counts (counts stay), chunk totals for the second level
+__global__ void __launch_bounds__(kScanThreads)
+k_cell_scan(const uint32_t* __restrict__ cell_count, uint32_t* __restrict__ cell_excl,
+            uint32_t* __restrict__ chunk_total, const GridDesc* __restrict__ desc, const StatusBlock* st) {
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  if (batch_failed(st)) return;
+  const int m = (int)desc->ncells;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  if (blockIdx.x * kScanChunk >= m) {  // beyond the table: contributes nothing to the second level
+    if (threadIdx.x == 0) chunk_total[blockIdx.x] = 0;
+    return;
+  }
+  uint32_t v[kScanItems];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (i0 + k < m) ? cell_count[i0 + k] : 0u;
+    tsum += v[k];
+  }
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t warp_excl = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    const uint32_t ws = warp_sums[w];
+    if (w < warp) warp_excl += ws;
+    total += ws;
+  }
+  uint32_t excl = warp_excl + (incl - tsum);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (i0 + k < m) cell_excl[i0 + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
+}
+
+// (start, end) of every table cell; the counters are zeroed for the next substep
+__global__ void __launch_bounds__(kThreads)
+k_cell_ranges(uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ cell_excl,
+              const uint32_t* __restrict__ chunk_total, int2* __restrict__ cell_range,
+              const GridDesc* __restrict__ desc, const StatusBlock* st) {
+  if (batch_failed(st)) return;
+  const uint32_t ncells = desc->ncells;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
+    const uint32_t cnt = cell_count[c];
+    const uint32_t start = cell_excl[c] + chunk_total[c / kScanChunk];  // chunk_total is an exclusive prefix by now
+    cell_range[c] = make_int2((int)start, (int)(start + cnt));
+    if (cnt) cell_count[c] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_cell_place(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ arrival,
+             const int2* __restrict__ cell_range, uint32_t* __restrict__ slot_id, const StatusBlock* st, NRef nr) {
+  if (batch_failed(st)) return;
+  const int n = nr.get();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  slot_id[(uint32_t)cell_range[keys[i]].x + arrival[i]] = (uint32_t)i;
+}
+
+// Thread per (unordered) slot: final slot = cell start + number of cell members with a smaller id.
+__global__ void __launch_bounds__(kThreads)
+k_cell_order(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slot_id,
+             const int2* __restrict__ cell_range, const float4* __restrict__ pred_o,
+             const float4* __restrict__ pos_o, uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ vals_sorted,
+             float4* __restrict__ pred_s, float4* __restrict__ pos_s, const StatusBlock* st, NRef nr) {
+  if (batch_failed(st)) return;
+  const int n = nr.get();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t id = slot_id[s];
+  const uint32_t key = keys[id];
+  const int2 r = cell_range[key];
+  int rank = 0;
+  for (int t = r.x; t < r.y; ++t) rank += slot_id[t] < id ? 1 : 0;
+  const int dst = r.x + rank;
+  const float4 q = pred_o[id];
+  const float4 p = pos_o[id];
+  keys_sorted[dst] = key;
+  vals_sorted[dst] = id;
+  pred_s[dst] = make_float4(q.x, q.y, q.z, 0.0f);
+  pos_s[dst] = make_float4(p.x, p.y, p.z, __uint_as_float(id));
+}
+
 // ---------------------------------------------------------------- a6 cell table + reorder
 __global__ void __launch_bounds__(kThreads)
 k_clear_cells(int2* __restrict__ cell_range, const GridDesc* __restrict__ desc, const StatusBlock* st) {
@@ -483,6 +600,21 @@ int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s) {
 
 int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, NRef n, int* out,
                 cudaStream_t s) {
+#if PBF_COUNTING_SORT
+  // keys[0] = key per particle, vals[0] = arrival slot inside its cell; the ordered result
+  // (keys[1], vals[1]) is written by launch_cells_reorder
+  k_cell_count<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(pred_o, g.keys[0], g.vals[0], g.cell_count, c.inv_h,
+                                                           g.desc, g.status, n);
+  const int nchunks = (int)((g.cell_cap + kScanChunk - 1) / kScanChunk);
+  k_cell_scan<<<nchunks, kScanThreads, 0, s>>>(g.cell_count, g.cell_excl, g.chunk_total, g.desc, g.status);
+  k_radix_scan_chunks<<<1, 1024, 0, s>>>(g.chunk_total, g.status, nchunks);
+  k_cell_ranges<<<148 * 8, kThreads, 0, s>>>(g.cell_count, g.cell_excl, g.chunk_total, g.cell_range, g.desc,
+                                            g.status);
+  k_cell_place<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(g.keys[0], g.vals[0], g.cell_range, g.slot_id,
+                                                           g.status, n);
+  *out = 1;
+  return 5;
+#else
   const int nblocks = sort_blocks(n.n);
   const int m = kRadixBins * nblocks;
   int launches = 0;
@@ -504,15 +636,23 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
   }
   *out = cur;
   return launches;
+#endif
 }
 
 int launch_cells_reorder(const uint32_t* keys, const uint32_t* vals, const float4* pred_o,
                          const float4* pos_o, float4* pred_s, float4* pos_s, const GridBuffers& g,
                          NRef n, cudaStream_t s) {
+#if PBF_COUNTING_SORT
+  (void)keys; (void)vals;
+  k_cell_order<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(g.keys[0], g.slot_id, g.cell_range, pred_o, pos_o,
+                                                           g.keys[1], g.vals[1], pred_s, pos_s, g.status, n);
+  return 1;
+#else
   k_clear_cells<<<148 * 4, kThreads, 0, s>>>(g.cell_range, g.desc, g.status);
   k_cells_reorder<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(keys, vals, pred_o, pos_o, pred_s, pos_s,
                                                               g.cell_range, g.status, n);
   return 2;
+#endif
 }
 
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,

@@ -24,6 +24,9 @@ struct GridBuffers {
   uint32_t* hist;       // kRadixBins * sort_blocks(n)
   uint32_t* chunk_total;  // one per 2048 hist entries
   int2* cell_range;     // cell_cap entries
+  uint32_t* cell_count; // cell_cap entries, zero between substeps (counting sort)
+  uint32_t* cell_excl;  // cell_cap entries: exclusive prefix inside a scan chunk
+  uint32_t* slot_id;    // n entries: particle id per slot before the cells are ordered by id
   uint32_t cell_cap;
   int sort_passes;      // ceil(log2(cell_cap) / 8)
 };

@@ -149,6 +149,14 @@ int ensure_tables(pbf_ctx* ctx) {
   if (ctx->cell_range.n < ctx->cell_cap) {
     invalidate_graph(ctx);
     PBF_CUDA(ctx, ctx->cell_range.reserve(ctx->cell_cap));
+    PBF_CUDA(ctx, ctx->cell_count.reserve(ctx->cell_cap));
+    PBF_CUDA(ctx, ctx->cell_excl.reserve(ctx->cell_cap));
+    // one chunk total per 2048 table cells (the radix scan needs far fewer)
+    PBF_CUDA(ctx, ctx->chunk_total.reserve(ctx->cell_cap / 2048 + 2 + (size_t)kRadixBins * sort_blocks((int)ctx->cap) / 2048));
+  }
+  if (ctx->slot_id.n < ctx->cap) {
+    invalidate_graph(ctx);
+    PBF_CUDA(ctx, ctx->slot_id.reserve(ctx->cap));
   }
   const size_t slots = ctx->slab.enabled ? ctx->slab.tot_cap : ctx->cap;
   const size_t need = ((slots + 31) / 32) * (size_t)ctx->K * 32u;
@@ -217,6 +225,9 @@ void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g) {
   g.hist = ctx->hist.p;
   g.chunk_total = ctx->chunk_total.p;
   g.cell_range = ctx->cell_range.p;
+  g.cell_count = ctx->cell_count.p;
+  g.cell_excl = ctx->cell_excl.p;
+  g.slot_id = ctx->slot_id.p;
   g.cell_cap = ctx->cell_cap;
   g.sort_passes = sort_passes_for(ctx->cell_cap);
 }
@@ -329,6 +340,9 @@ int reset_status(pbf_ctx* ctx) {
   for (int a = 0; a < 3; ++a) { z.min_cell[a] = INT_MAX; z.max_cell[a] = INT_MIN; }
   *ctx->status_host = z;
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status.p, ctx->status_host, sizeof(StatusBlock), cudaMemcpyHostToDevice, ctx->stream));
+  // the per-cell counters are zero between substeps; a batch that failed half-way may have left some
+  if (ctx->cell_count.p)
+    PBF_CUDA(ctx, cudaMemsetAsync(ctx->cell_count.p, 0, ctx->cell_count.n * sizeof(uint32_t), ctx->stream));
   return PBF_OK;
 }
 
@@ -430,6 +444,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->vel_a.release(); ctx->vel_b.release(); ctx->omega.release(); ctx->rho.release();
   ctx->planes_dev.release(); ctx->desc.release(); ctx->status.release();
   ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
+  ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release();
   ctx->hist.release(); ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();

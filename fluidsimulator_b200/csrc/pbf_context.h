@@ -138,6 +138,7 @@ struct pbf_ctx {
   pbf::DevBuf<pbf::StatusBlock> status;
   pbf::DevBuf<uint32_t> keys0, keys1, vals0, vals1, hist, chunk_total;
   pbf::DevBuf<int2> cell_range;
+  pbf::DevBuf<uint32_t> cell_count, cell_excl, slot_id;
   uint32_t cell_cap = 1u << 22;
   int sorted_buf = 0;  // which keys/vals buffer holds the last substep's sorted order
   // neighbour list
