@@ -492,6 +492,48 @@ k_cells_reorder(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
 // sums of products use scalar adds, see pbf_device.cuh).  Entry k of particle i lives at
 // idx[(i/32)*K*32 + (k/2)*64 + (i%32)*2 + k%2]: a solver pass reads two entries per lane
 // with one 8-byte load, 256 contiguous bytes per warp.
+// The kernel is issue-bound (73 % issue-active, 19 of 32 lanes busy on average: lanes of a warp
+// sit in ~5 different cells whose stencil cells hold different numbers of particles).  The hit
+// path is kept short — a running element offset instead of re-deriving the list address, and only
+// the centre cell pays for the j != i test.  Three restructurings that remove the divergence
+// (flattened walk, warp per cell, tests in memory order + bitmasks) were measured and are slower,
+// see DESIGN.md §4.
+struct NbrEmit {
+  uint32_t* out;
+  uint32_t cnt, off;  // entries so far; element offset of entry `cnt`: (cnt / 2) * 64 + cnt % 2
+  uint32_t K;
+  __device__ __forceinline__ void put(bool hit, int j) {
+    if (hit && cnt < K) __stcs(out + off, (uint32_t)j);
+    off += hit ? ((cnt & 1u) ? 63u : 1u) : 0u;
+    cnt += hit ? 1u : 0u;
+  }
+};
+
+template <bool CENTER>
+__device__ __forceinline__ void neighbors_cell(const float4* __restrict__ pred_s, int2 range, float4 pi, f2 pxy, int i,
+                                               float h2, NbrEmit& e) {
+  for (int j = range.x; j < range.y; j += 2) {
+    const bool v1 = (j + 1) < range.y;
+    const float4 a0 = pred_s[j];
+    const float4 a1 = pred_s[v1 ? j + 1 : j];
+    // x and y of ONE candidate share an f32x2 (they sit in an aligned register pair after
+    // the 16-byte load: no packing moves), z is scalar; same roundings as (dx*dx + dy*dy) + dz*dz
+    const f2 d0 = __fadd2_rn(pxy, make_float2(-a0.x, -a0.y));
+    const f2 d1 = __fadd2_rn(pxy, make_float2(-a1.x, -a1.y));
+    const float z0 = __fsub_rn(pi.z, a0.z), z1 = __fsub_rn(pi.z, a1.z);
+    const f2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
+    const float r2a = __fadd_rn(__fadd_rn(q0.x, q0.y), __fmul_rn(z0, z0));
+    const float r2b = __fadd_rn(__fadd_rn(q1.x, q1.y), __fmul_rn(z1, z1));
+    bool h0 = r2a < h2, h1 = v1 && (r2b < h2);  // core.cpp:231-240
+    if (CENTER) {
+      h0 = h0 && (j != i);
+      h1 = h1 && (j + 1 != i);
+    }
+    e.put(h0, j);
+    e.put(h1, j + 1);
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
             const GridDesc* __restrict__ desc, uint32_t* __restrict__ nbr_idx,
@@ -516,42 +558,28 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
     if (!active) nbr_count[i] = 0;
   }
   if (active) {
-    uint32_t* out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
+    NbrEmit e;
+    e.out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
+    e.cnt = 0;
+    e.off = 0;
+    e.K = (uint32_t)K;
     const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
     const f2 pxy = make_float2(pi.x, pi.y);
+#pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll 1
       for (int dy = -1; dy <= 1; ++dy) {
         const uint32_t row = ((uint32_t)(cx - 1) * (uint32_t)dimy + (uint32_t)(cy + dy)) * (uint32_t)dimz +
                              (uint32_t)(cz + dz);
-        int2 range[3];
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) range[dx] = cell_range[row + (uint32_t)dx * xstride];
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          for (int j = range[dx].x; j < range[dx].y; j += 2) {
-            const bool v1 = (j + 1) < range[dx].y;
-            const int j1 = v1 ? j + 1 : j;
-            const float4 a0 = pred_s[j];
-            const float4 a1 = pred_s[j1];
-            // x and y of ONE candidate share an f32x2 (they sit in an aligned register pair after
-            // the 16-byte load: no packing moves), z is scalar; same roundings as (dx*dx + dy*dy) + dz*dz
-            const f2 d0 = __fadd2_rn(pxy, make_float2(-a0.x, -a0.y));
-            const f2 d1 = __fadd2_rn(pxy, make_float2(-a1.x, -a1.y));
-            const float z0 = __fsub_rn(pi.z, a0.z), z1 = __fsub_rn(pi.z, a1.z);
-            const f2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
-            const float r2a = __fadd_rn(__fadd_rn(q0.x, q0.y), __fmul_rn(z0, z0));
-            const float r2b = __fadd_rn(__fadd_rn(q1.x, q1.y), __fmul_rn(z1, z1));
-            if (j != i && r2a < h2) {  // core.cpp:231-240
-              if (cnt < (uint32_t)K) __stcs(out + (size_t)(cnt >> 1) * 64u + (cnt & 1u), (uint32_t)j);
-              ++cnt;
-            }
-            if (v1 && j1 != i && r2b < h2) {
-              if (cnt < (uint32_t)K) __stcs(out + (size_t)(cnt >> 1) * 64u + (cnt & 1u), (uint32_t)j1);
-              ++cnt;
-            }
-          }
-        }
+        const int2 r0 = cell_range[row], r1 = cell_range[row + xstride], r2 = cell_range[row + 2u * xstride];
+        neighbors_cell<false>(pred_s, r0, pi, pxy, i, h2, e);
+        if (dz == 0 && dy == 0)
+          neighbors_cell<true>(pred_s, r1, pi, pxy, i, h2, e);
+        else
+          neighbors_cell<false>(pred_s, r1, pi, pxy, i, h2, e);
+        neighbors_cell<false>(pred_s, r2, pi, pxy, i, h2, e);
       }
+    cnt = e.cnt;
     nbr_count[i] = cnt < (uint32_t)K ? cnt : (uint32_t)K;
   }
   // batch statistic: max count (to size K)
