@@ -227,6 +227,12 @@ def run_ours(args, flags):
         launches = sol.launch_count() - launches0
         nbr_total = sol.debug_sizes()[1]
 
+        # With vorticity on the REFERENCE trajectory blows up after a few substeps: every
+        # phase then restarts from t0 so that no phase runs deeper into the blow-up than the timed one.
+        restart = bool(flags["vort"])
+        if restart:
+            sol.upload(state)
+            sol.step(args.warmup)
         # per-stage CUDA-event timing of the same K substeps' successors (profiling disables the graph)
         sol.profile_enable(True)
         sol.profile_reset()
@@ -240,8 +246,12 @@ def run_ours(args, flags):
         sol.profile_enable(False)
 
         # e2e: the reference-facing call (cuda_step contract): pinned host arrays in and out every step
+        if restart:
+            sol.upload(state)
         host = [torch.from_numpy(a).pin_memory().numpy() for a in sol.download()]
         e2e_steps = max(3, min(args.steps, 20))
+        if restart:
+            e2e_steps = min(e2e_steps, args.steps)
         sol.step_host(host, 1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -301,7 +311,7 @@ def run_ours(args, flags):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default=None)

@@ -561,7 +561,7 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
   // batch backup: a substep that overflows a device table is re-run after growing it
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_bak.p, ctx->pos_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-  for (int attempt = 0; attempt < 12; ++attempt) {
+  for (int attempt = 0; attempt < 32; ++attempt) {
     int rc = ensure_tables(ctx);
     if (rc != PBF_OK) return rc;
     if ((rc = reset_status(ctx)) != PBF_OK) return rc;
@@ -596,12 +596,14 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
       invalidate_graph(ctx);
     }
     if (st.nbr_overflow) {
-      const unsigned need = st.max_neighbors + st.max_neighbors / 4 + 8;
+      // the batch stops at the first overflowing substep, so the maximum seen is a lower bound of
+      // what the rest of the batch needs: grow by half, not by a sliver
+      const unsigned need = st.max_neighbors + st.max_neighbors / 2 + 16;
       ctx->K = (int)((need + 7u) & ~7u);
       invalidate_graph(ctx);
     }
   }
-  return fail(ctx, PBF_E_CAPACITY, "pbf_step: device tables kept overflowing after 12 growth attempts");
+  return fail(ctx, PBF_E_CAPACITY, "pbf_step: device tables kept overflowing after 32 growth attempts");
 }
 
 int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz, int nsteps) {

@@ -621,7 +621,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     PBF_CUDA(ctx, cudaMemcpyAsync(sl.gid_bak.p, sl.gid_o.p, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  for (int attempt = 0; attempt < 16; ++attempt) {
+  for (int attempt = 0; attempt < 32; ++attempt) {
     if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;
     if ((rc = ensure_tables(ctx)) != PBF_OK) return rc;
     if ((rc = sl.transport->prepare(ctx, sl.msg_elems)) != PBF_OK) {  // last: may end in a barrier
@@ -724,7 +724,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       while ((unsigned long long)cap < max_cells + max_cells / 4) cap <<= 1;
       ctx->cell_cap = cap;
     }
-    if (st.nbr_overflow) ctx->K = (int)((st.max_neighbors + st.max_neighbors / 4 + 8 + 7u) & ~7u);
+    if (st.nbr_overflow) ctx->K = (int)((st.max_neighbors + st.max_neighbors / 2 + 16 + 7u) & ~7u);
     if (st.mig_overflow) sl.mcap = (int)(st.max_send + st.max_send / 2 + 1024);
     if (st.ghost_overflow) sl.gcap = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
     // far_migrant only counts when nothing else went wrong (a slab that stopped early leaves its
@@ -748,7 +748,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       PBF_CUDA(ctx, cudaMemcpyAsync(sl.gid_o.p, sl.gid_bak.p, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     }
   }
-  return fail(ctx, PBF_E_CAPACITY, "pbf_step: slab tables kept overflowing after 16 growth attempts");
+  return fail(ctx, PBF_E_CAPACITY, "pbf_step: slab tables kept overflowing after 32 growth attempts");
 }
 
 }  // namespace pbf
