@@ -173,6 +173,10 @@ def bench(args, flags, rank: int, world: int, local: int):
         e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
 
+    # every rank's per-stage split (interior slabs carry two ghost sides, edge slabs one)
+    my_stages = {k: v["ms"] / psteps for k, v in prof.items() if v["launches"]}
+    all_stages = [None] * world
+    dist.all_gather_object(all_stages, my_stages)
     tot_launch = torch.tensor([launches], dtype=torch.int64, device=device)
     dist.all_reduce(tot_launch)
     owned_t = torch.zeros(world, dtype=torch.int64, device=device)
@@ -208,6 +212,7 @@ def bench(args, flags, rank: int, world: int, local: int):
                 "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
                 "call": "per rank: pbf_slab_upload_owned + pbf_step(1) + pbf_slab_download"},
         "gpu_launches": int(tot_launch.item()), "clocks": clocks, "stages": stages,
+        "stages_per_rank_ms": [{k: round(v, 4) for k, v in st.items()} for st in all_stages],
         "exchange": {"per_substep": (stats1["exchanges"] - stats0["exchanges"]) / args.steps,
                      "bytes_per_substep_rank0": (stats1["bytes_sent"] - stats0["bytes_sent"]) / args.steps,
                      "ghosts_rank0": stats1["ghosts"], "hops": stats1["hops"]},
