@@ -25,9 +25,6 @@ namespace pbf {
 namespace {
 
 constexpr int kThreads = 256;
-#ifndef PBF_COUNTING_SORT
-#define PBF_COUNTING_SORT 1
-#endif
 // ---------------------------------------------------------------- state (de)interleave
 __global__ void __launch_bounds__(kThreads)
 k_pack_state(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
@@ -80,7 +77,7 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
     lo[1] = min(lo[1], cy); hi[1] = max(hi[1], cy);
     lo[2] = min(lo[2], cz); hi[2] = max(hi[2], cz);
   }
-  if (!do_bounds) return;  // slab mode: the bounds are taken after migration (k_slab_merge)
+  if (!do_bounds) return;
   // block-level reduction first: six pre-checked atomics per BLOCK.  (Per-warp atomics made every
   // warp poll the same L2 line; with one particle per thread that serialised the whole kernel.)
   __shared__ int s_lo[3][kThreads / 32], s_hi[3][kThreads / 32];
@@ -152,95 +149,14 @@ __device__ __forceinline__ uint32_t dense_key(float4 q, float inv_h, const GridD
   return ((uint32_t)cx * (uint32_t)d.dim[1] + (uint32_t)cy) * (uint32_t)d.dim[2] + (uint32_t)cz;
 }
 
-// keys in ORIGINAL particle order + the per-block digit histogram of radix pass 0.
-__global__ void __launch_bounds__(kThreads)
-k_keys_hist(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist,
-            float inv_h, const GridDesc* __restrict__ desc, const StatusBlock* st, NRef nr, int nblocks) {
-  __shared__ uint32_t sh[kRadixBins];
-  if (batch_failed(st)) return;
-  const int n = nr.get();
-  const GridDesc d = *desc;
-  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) sh[b] = 0;
-  __syncthreads();
-  const int base = blockIdx.x * kSortTile;
-#pragma unroll
-  for (int r = 0; r < kSortTile / kThreads; ++r) {
-    const int i = base + r * kThreads + threadIdx.x;
-    if (i < n) {
-      const uint32_t k = dense_key(pred_o[i], inv_h, d);
-      keys[i] = k;
-      atomicAdd(&sh[k & (kRadixBins - 1)], 1u);
-    }
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) hist[b * nblocks + blockIdx.x] = sh[b];
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_radix_hist(const uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, const StatusBlock* st,
-             NRef nr, int nblocks, int shift) {
-  __shared__ uint32_t sh[kRadixBins];
-  if (batch_failed(st)) return;
-  const int n = nr.get();
-  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) sh[b] = 0;
-  __syncthreads();
-  const int base = blockIdx.x * kSortTile;
-#pragma unroll
-  for (int r = 0; r < kSortTile / kThreads; ++r) {
-    const int i = base + r * kThreads + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < kRadixBins; b += kThreads) hist[b * nblocks + blockIdx.x] = sh[b];
-}
-
-// Exclusive scan of hist[digit*nblocks + block], two levels: every block scans one chunk of
-// kScanChunk entries in place and publishes the chunk total; the consumer (k_radix_scatter)
-// adds the exclusive prefix of the chunk totals, which it recomputes in shared memory (there
-// are only m / kScanChunk of them).
+// Two-level exclusive scan helpers: a block scans one chunk of kScanChunk entries and publishes
+// the chunk total; k_scan_chunks turns the totals into exclusive prefixes.
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanChunk = kScanThreads * kScanItems;  // 2048 entries per block
-__global__ void __launch_bounds__(kScanThreads)
-k_radix_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ chunk_total, const StatusBlock* st, int m) {
-  __shared__ uint32_t warp_sums[kScanThreads / 32];
-  if (batch_failed(st)) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
-  uint32_t v[kScanItems];
-  uint32_t tsum = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    v[k] = (i0 + k < m) ? hist[i0 + k] : 0u;
-    tsum += v[k];
-  }
-  uint32_t incl = tsum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  uint32_t warp_excl = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w) {
-    const uint32_t ws = warp_sums[w];
-    if (w < warp) warp_excl += ws;
-    total += ws;
-  }
-  uint32_t excl = warp_excl + (incl - tsum);
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    if (i0 + k < m) hist[i0 + k] = excl;
-    excl += v[k];
-  }
-  if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
-}
-
 // Exclusive scan of the chunk totals, in place (one block; there are m / kScanChunk of them).
 __global__ void __launch_bounds__(1024)
-k_radix_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nchunks) {
+k_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nchunks) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_sh;
   if (batch_failed(st)) return;
@@ -277,78 +193,16 @@ k_radix_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, i
   }
 }
 
-// Stable scatter of one radix pass.  Tile order is (warp, round, lane) == memory order;
-// ranks come from __match_any_sync peer groups plus per-warp digit counters.
-__global__ void __launch_bounds__(kThreads)
-k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ chunk_total,
-                const StatusBlock* st, NRef nr, int nblocks, int shift) {
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kRounds = kSortTile / kThreads;  // per warp: kRounds x 32 consecutive keys
-  __shared__ uint32_t whist[kWarps][kRadixBins];
-  __shared__ uint32_t digit_base[kRadixBins];
-  if (batch_failed(st)) return;
-  const int n = nr.get();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int b = threadIdx.x; b < kWarps * kRadixBins; b += kThreads) (&whist[0][0])[b] = 0;
-  // global base of (digit, this block) = in-chunk exclusive scan + sum of the earlier chunk totals
-  for (int d = threadIdx.x; d < kRadixBins; d += kThreads) {
-    const int e = d * nblocks + blockIdx.x;
-    digit_base[d] = offsets[e] + chunk_total[e / kScanChunk];  // chunk_total is already an exclusive prefix
-  }
-  __syncthreads();
-
-  const int warp_base = blockIdx.x * kSortTile + warp * (kRounds * 32);
-  uint32_t key[kRounds], val[kRounds], rank[kRounds];
-  const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-  for (int r = 0; r < kRounds; ++r) {
-    const int i = warp_base + r * 32 + lane;
-    const bool valid = i < n;
-    key[r] = valid ? keys_in[i] : 0u;
-    val[r] = valid ? (vals_in ? vals_in[i] : (uint32_t)i) : 0u;
-    const uint32_t d = valid ? ((key[r] >> shift) & (kRadixBins - 1)) : (uint32_t)kRadixBins;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const uint32_t below = __popc(peers & lt_mask);
-    const uint32_t prev = valid ? whist[warp][d] : 0u;
-    __syncwarp();
-    if (valid && below == 0) whist[warp][d] = prev + __popc(peers);
-    __syncwarp();
-    rank[r] = prev + below;
-  }
-  __syncthreads();
-  // per digit: global base of this block, then exclusive scan over the warps
-  for (int d = threadIdx.x; d < kRadixBins; d += kThreads) {
-    uint32_t running = digit_base[d];
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const uint32_t cnt = whist[w][d];
-      whist[w][d] = running;
-      running += cnt;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < kRounds; ++r) {
-    const int i = warp_base + r * 32 + lane;
-    if (i < n) {
-      const uint32_t d = (key[r] >> shift) & (kRadixBins - 1);
-      const uint32_t pos = whist[warp][d] + rank[r];
-      keys_out[pos] = key[r];
-      vals_out[pos] = val[r];
-    }
-  }
-}
-
 // ---------------------------------------------------------------- a5 + a6 as a counting sort
 // The key is a dense cell index, so the sort of core.cpp:173-183 plus the run-length table of
 // core.cpp:185-203 is a counting sort: count per cell, exclusive scan = cell starts (= the table),
 // place.  The reference order inside a cell is ascending particle id (core.cpp:182); atomics hand
 // out arrival slots in arbitrary order, so the last kernel ranks every particle among the (few)
 // members of its cell by id — O(occupancy) reads per particle — and writes the final slot together
-// with the gathered positions.  6 launches instead of 14 for the 3-pass radix sort + table, and the
-// result is bit-identical to it (kept below as the reference implementation, PBF_COUNTING_SORT=0).
+// with the gathered positions.  6 launches instead of the 14 of the 3-pass stable radix sort + table
+// this replaced (same bits, 105 -> 55 us at 1 M particles).  In slab mode "particle id" is the
+// GLOBAL id (gid): the storage order of a slab's particles is then irrelevant, which is what lets
+// migration fill holes instead of re-packing the slab (kernels/slab.cu).
 __global__ void __launch_bounds__(kThreads)
 k_cell_count(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ arrival,
              uint32_t* __restrict__ cell_count, float inv_h, const GridDesc* __restrict__ desc,
@@ -436,7 +290,8 @@ __global__ void __launch_bounds__(kThreads)
 k_cell_order(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slot_id,
              const int2* __restrict__ cell_range, const float4* __restrict__ pred_o,
              const float4* __restrict__ pos_o, uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ vals_sorted,
-             float4* __restrict__ pred_s, float4* __restrict__ pos_s, const StatusBlock* st, NRef nr) {
+             float4* __restrict__ pred_s, float4* __restrict__ pos_s, const uint32_t* __restrict__ gid,
+             const StatusBlock* st, NRef nr) {
   if (batch_failed(st)) return;
   const int n = nr.get();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,7 +300,12 @@ k_cell_order(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slo
   const uint32_t key = keys[id];
   const int2 r = cell_range[key];
   int rank = 0;
-  for (int t = r.x; t < r.y; ++t) rank += slot_id[t] < id ? 1 : 0;
+  if (gid) {  // slab: the reference's particle id is the global one
+    const uint32_t g = gid[id];
+    for (int t = r.x; t < r.y; ++t) rank += gid[slot_id[t]] < g ? 1 : 0;
+  } else {
+    for (int t = r.x; t < r.y; ++t) rank += slot_id[t] < id ? 1 : 0;
+  }
   const int dst = r.x + rank;
   const float4 q = pred_o[id];
   const float4 p = pos_o[id];
@@ -453,36 +313,6 @@ k_cell_order(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slo
   vals_sorted[dst] = id;
   pred_s[dst] = make_float4(q.x, q.y, q.z, 0.0f);
   pos_s[dst] = make_float4(p.x, p.y, p.z, __uint_as_float(id));
-}
-
-// ---------------------------------------------------------------- a6 cell table + reorder
-__global__ void __launch_bounds__(kThreads)
-k_clear_cells(int2* __restrict__ cell_range, const GridDesc* __restrict__ desc, const StatusBlock* st) {
-  if (batch_failed(st)) return;
-  const uint32_t ncells = desc->ncells;
-  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x)
-    cell_range[c] = make_int2(0, 0);
-}
-
-// Sorted slot i: run boundaries -> cell_range (core.cpp:185-203), and gather of the
-// predicted / committed positions into sorted order (the reorder of north_star).
-__global__ void __launch_bounds__(kThreads)
-k_cells_reorder(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                const float4* __restrict__ pred_o, const float4* __restrict__ pos_o,
-                float4* __restrict__ pred_s, float4* __restrict__ pos_s,
-                int2* __restrict__ cell_range, const StatusBlock* st, NRef nr) {
-  if (batch_failed(st)) return;
-  const int n = nr.get();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t k = keys[i];
-  const uint32_t o = vals[i];
-  if (i == 0 || keys[i - 1] != k) cell_range[k].x = i;
-  if (i == n - 1 || keys[i + 1] != k) cell_range[k].y = i + 1;
-  const float4 q = pred_o[o];
-  const float4 p = pos_o[o];
-  pred_s[i] = make_float4(q.x, q.y, q.z, 0.0f);
-  pos_s[i] = make_float4(p.x, p.y, p.z, __uint_as_float(o));
 }
 
 // ---------------------------------------------------------------- a7 neighbour list
@@ -615,8 +445,8 @@ int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConst
   // stream at HBM speed, few enough warps that the six bound atomics stay cheap
   int blocks = grid_for(n.n, kThreads);
   if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
-  k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n, slab ? 0 : 1);
-  if (slab) return 1;  // bounds + table descriptor follow the migration (launch_grid_finalize)
+  k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n, 1);
+  if (slab) return 1;  // migrants extend the bounds; the table descriptor follows (launch_grid_finalize)
   k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap, 1);
   return 2;
 }
@@ -628,59 +458,26 @@ int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s) {
 
 int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, NRef n, int* out,
                 cudaStream_t s) {
-#if PBF_COUNTING_SORT
   // keys[0] = key per particle, vals[0] = arrival slot inside its cell; the ordered result
   // (keys[1], vals[1]) is written by launch_cells_reorder
   k_cell_count<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(pred_o, g.keys[0], g.vals[0], g.cell_count, c.inv_h,
                                                            g.desc, g.status, n);
   const int nchunks = (int)((g.cell_cap + kScanChunk - 1) / kScanChunk);
   k_cell_scan<<<nchunks, kScanThreads, 0, s>>>(g.cell_count, g.cell_excl, g.chunk_total, g.desc, g.status);
-  k_radix_scan_chunks<<<1, 1024, 0, s>>>(g.chunk_total, g.status, nchunks);
+  k_scan_chunks<<<1, 1024, 0, s>>>(g.chunk_total, g.status, nchunks);
   k_cell_ranges<<<148 * 8, kThreads, 0, s>>>(g.cell_count, g.cell_excl, g.chunk_total, g.cell_range, g.desc,
                                             g.status);
   k_cell_place<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(g.keys[0], g.vals[0], g.cell_range, g.slot_id,
                                                            g.status, n);
   *out = 1;
   return 5;
-#else
-  const int nblocks = sort_blocks(n.n);
-  const int m = kRadixBins * nblocks;
-  int launches = 0;
-  int cur = 0;
-  for (int pass = 0; pass < g.sort_passes; ++pass) {
-    const int shift = pass * kRadixBits;
-    if (pass == 0)
-      k_keys_hist<<<nblocks, kThreads, 0, s>>>(pred_o, g.keys[0], g.hist, c.inv_h, g.desc, g.status, n, nblocks);
-    else
-      k_radix_hist<<<nblocks, kThreads, 0, s>>>(g.keys[cur], g.hist, g.status, n, nblocks, shift);
-    const int nchunks = (m + kScanChunk - 1) / kScanChunk;
-    k_radix_scan<<<nchunks, kScanThreads, 0, s>>>(g.hist, g.chunk_total, g.status, m);
-    k_radix_scan_chunks<<<1, 1024, 0, s>>>(g.chunk_total, g.status, nchunks);
-    k_radix_scatter<<<nblocks, kThreads, 0, s>>>(g.keys[cur], pass == 0 ? nullptr : g.vals[cur],
-                                                g.keys[cur ^ 1], g.vals[cur ^ 1], g.hist, g.chunk_total,
-                                                g.status, n, nblocks, shift);
-    cur ^= 1;
-    launches += 4;
-  }
-  *out = cur;
-  return launches;
-#endif
 }
 
-int launch_cells_reorder(const uint32_t* keys, const uint32_t* vals, const float4* pred_o,
-                         const float4* pos_o, float4* pred_s, float4* pos_s, const GridBuffers& g,
-                         NRef n, cudaStream_t s) {
-#if PBF_COUNTING_SORT
-  (void)keys; (void)vals;
+int launch_cells_reorder(const float4* pred_o, const float4* pos_o, float4* pred_s, float4* pos_s,
+                         const uint32_t* gid, const GridBuffers& g, NRef n, cudaStream_t s) {
   k_cell_order<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(g.keys[0], g.slot_id, g.cell_range, pred_o, pos_o,
-                                                           g.keys[1], g.vals[1], pred_s, pos_s, g.status, n);
+                                                           g.keys[1], g.vals[1], pred_s, pos_s, gid, g.status, n);
   return 1;
-#else
-  k_clear_cells<<<148 * 4, kThreads, 0, s>>>(g.cell_range, g.desc, g.status);
-  k_cells_reorder<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(keys, vals, pred_o, pos_o, pred_s, pos_s,
-                                                              g.cell_range, g.status, n);
-  return 2;
-#endif
 }
 
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,

@@ -10,25 +10,17 @@
 
 namespace pbf {
 
-constexpr int kRadixBits = 8;
-constexpr int kRadixBins = 1 << kRadixBits;
-constexpr int kSortTile = 2048;  // keys per block in the radix passes
-
-inline int sort_blocks(int n) { return (n + kSortTile - 1) / kSortTile; }
-
 struct GridBuffers {
   GridDesc* desc;
   StatusBlock* status;
   uint32_t* keys[2];
   uint32_t* vals[2];
-  uint32_t* hist;       // kRadixBins * sort_blocks(n)
-  uint32_t* chunk_total;  // one per 2048 hist entries
+  uint32_t* chunk_total;  // one per 2048 table cells
   int2* cell_range;     // cell_cap entries
   uint32_t* cell_count; // cell_cap entries, zero between substeps (counting sort)
   uint32_t* cell_excl;  // cell_cap entries: exclusive prefix inside a scan chunk
   uint32_t* slot_id;    // n entries: particle id per slot before the cells are ordered by id
   uint32_t cell_cap;
-  int sort_passes;      // ceil(log2(cell_cap) / 8)
 };
 
 struct NeighborList {
@@ -46,14 +38,13 @@ int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const s
 int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConsts& c,
                    const GridBuffers& g, NRef n, bool slab, cudaStream_t s);
 int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s);
-// a4+a5: dense keys + LSD radix sort (stable => ties keep ascending particle id).
-// On return the sorted keys/vals are in g.keys[out]/g.vals[out]; returns launches, sets *out.
+// a4+a5+a6: dense keys, counting sort by cell, cell start/end table.  launch_cells_reorder then
+// orders every cell by particle id (`gid` = global ids in slab mode, nullptr = the slot index),
+// writes the sorted keys / ids to g.keys[*out] / g.vals[*out] and gathers pred/pos into sorted order.
 int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g, NRef n,
                 int* out, cudaStream_t s);
-// a6 + reorder: dense cell start/end table, gather pred/pos into sorted order.
-int launch_cells_reorder(const uint32_t* keys, const uint32_t* vals, const float4* pred_o,
-                         const float4* pos_o, float4* pred_s, float4* pos_s,
-                         const GridBuffers& g, NRef n, cudaStream_t s);
+int launch_cells_reorder(const float4* pred_o, const float4* pos_o, float4* pred_s, float4* pos_s,
+                         const uint32_t* gid, const GridBuffers& g, NRef n, cudaStream_t s);
 // a7: neighbour list in the oracle's traversal order.
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,
                      const NeighborList& nl, NRef n, cudaStream_t s);
@@ -99,9 +90,8 @@ int launch_commit_only(const SolveBuffers& b, const StepConsts& c, NRef n, bool 
 struct SlabBuffers {
   SlabCounts* counts;       // device
   StatusBlock* status;
-  uint32_t* gid_o;          // global particle id per owned slot (ascending)
-  float4 *keep_pos, *keep_pred;  // staging of the particles that stay (pos.w = bits(gid))
-  uint32_t* blk_cnt;        // 3 * blocks(cap) class counters
+  uint32_t* gid_o;          // global particle id per owned slot (any order)
+  uint32_t* holes;          // 6 * mcap: vacated slots, then two scratch lists of 2 * mcap each
   float4* send[2];          // message to the left / right neighbour
   float4* recv[2];          // message from the left / right neighbour
   int cut_lo, cut_hi;       // owned x-cells [cut_lo, cut_hi); INT_MIN / INT_MAX at the ends
@@ -110,11 +100,12 @@ struct SlabBuffers {
   int mcap;                 // migration message capacity (particles)
   int gcap;                 // ghost message capacity (particles)
 };
-// migration, one hop: classify by predicted x-cell, stable 3-way split, pack the two messages
-int launch_slab_split(const float4* pos_o, const float4* pred_o, const SlabBuffers& sb, const StepConsts& c,
+// migration, one hop: particles whose predicted x-cell left the slab go into the two messages and
+// the slots they vacate are refilled from the tail of the owned range (O(migrants) data movement)
+int launch_slab_split(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c,
                       cudaStream_t s);
-// merge kept + received particles by ascending global id into pos_o/pred_o/gid_o; on the last hop
-// also takes the cell bounds and flags particles that are still outside the slab
+// append the received particles; on the last hop also extends the cell bounds by them and flags
+// arrivals that are still outside the slab
 int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, bool last_hop,
                       cudaStream_t s);
 // boundary counts + ghost messages (pred, pos of the two boundary layers on each side)

@@ -3,9 +3,9 @@
 // The reference has no multi-GPU path; what pins this file is the single-GPU result: the
 // reference's sort order is x-major (cell_key_less, reference core/src/core.cpp:12-21), so the
 // particles of the x-cells [cut_lo, cut_hi) are one contiguous range of the global sorted order.
-// Everything here preserves two invariants that make the slab result BIT-IDENTICAL to one GPU:
-//   (1) owned particles are stored in ascending global id, so the stable radix sort breaks ties
-//       inside a cell exactly like the reference (core.cpp:182);
+// Two things make the slab result BIT-IDENTICAL to one GPU:
+//   (1) the counting sort orders the members of a cell by GLOBAL particle id (k_cell_order), which
+//       is the reference's tie-break (core.cpp:182) whatever order a slab stores its particles in;
 //   (2) ghosts are appended in the sender's sorted order, so ghost cells list their particles in
 //       ascending id as well.
 // All counts live in device memory (SlabCounts); messages have a fixed capacity and carry their
@@ -32,225 +32,121 @@ __device__ __forceinline__ int slab_class(float x, float inv_h, int cut_lo, int 
   return cx < cut_lo ? 1 : (cx >= cut_hi ? 2 : 0);
 }
 
-// ---------------------------------------------------------------- migration: split
+// ---------------------------------------------------------------- migration
+// The order in which a slab stores its particles is irrelevant (cells are ordered by global id in
+// k_cell_order), so migration moves O(migrants) data: leavers are copied into the messages and
+// their slots recorded; the vacated slots below the new end are refilled with the stayers of the
+// tail; arrivals are appended.  Only k_slab_leave touches every particle (one 16-byte read).
 __global__ void __launch_bounds__(kThreads)
-k_slab_count(const float4* __restrict__ pred_o, const SlabCounts* __restrict__ counts, uint32_t* __restrict__ blk_cnt,
-             const StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int nblocks) {
-  __shared__ uint32_t wc[3][kThreads / 32];
+k_slab_leave(const float4* __restrict__ pos_o, const float4* __restrict__ pred_o, const uint32_t* __restrict__ gid_o,
+             SlabCounts* __restrict__ counts, uint32_t* __restrict__ holes, float4* __restrict__ send_l,
+             float4* __restrict__ send_r, const StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int mcap) {
   if (batch_failed(st)) return;
-  const int n = counts->n_own;
   const int i = blockIdx.x * kThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cls = (i < n) ? slab_class(pred_o[i].x, inv_h, cut_lo, cut_hi) : 3;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
-    if (lane == 0) wc[c][warp] = __popc(m);
+  if (i >= counts->n_own) return;
+  const float4 q = pred_o[i];
+  const int cls = slab_class(q.x, inv_h, cut_lo, cut_hi);
+  if (cls == 0) return;
+  const int k = atomicAdd(&counts->n_send[cls - 1], 1);
+  if (k < mcap) {
+    float4* msg = (cls == 1) ? send_l : send_r;
+    const float4 p = pos_o[i];
+    msg[1 + k] = make_float4(p.x, p.y, p.z, __uint_as_float(gid_o[i]));
+    msg[1 + mcap + k] = make_float4(q.x, q.y, q.z, 0.0f);
   }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    uint32_t t = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) t += wc[threadIdx.x][w];
-    blk_cnt[threadIdx.x * nblocks + blockIdx.x] = t;
-  }
+  const int h = atomicAdd(&counts->n_holes, 1);
+  if (h < 2 * mcap) holes[h] = (uint32_t)i;
 }
 
-// Exclusive scan of the three per-block counter rows (one block), totals -> SlabCounts + headers.
+// One block: message headers, then holes below the new end <- stayers of the tail.
 __global__ void __launch_bounds__(1024)
-k_slab_scan(uint32_t* __restrict__ blk_cnt, SlabCounts* __restrict__ counts, StatusBlock* st, float4* send_l,
-            float4* send_r, int nblocks, int mcap) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_sh;
+k_slab_refill(float4* __restrict__ pos_o, float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o,
+              SlabCounts* __restrict__ counts, uint32_t* __restrict__ holes, float4* send_l, float4* send_r,
+              StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int mcap) {
+  __shared__ int s_a, s_b;
   if (batch_failed(st)) {
     if (threadIdx.x == 0) send_l[0] = send_r[0] = hdr_fail();
     return;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = 0; c < 3; ++c) {
-    uint32_t* row = blk_cnt + (size_t)c * nblocks;
-    if (threadIdx.x == 0) carry_sh = 0;
-    __syncthreads();
-    for (int base = 0; base < nblocks; base += 1024) {
-      const int i = base + threadIdx.x;
-      const uint32_t v = (i < nblocks) ? row[i] : 0u;
-      uint32_t incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (lane == 31) warp_sums[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        const uint32_t w = warp_sums[lane];
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-          if (lane >= o) wi += t;
-        }
-        warp_sums[lane] = wi - w;
-      }
-      __syncthreads();
-      const uint32_t excl = carry_sh + warp_sums[warp] + (incl - v);
-      if (i < nblocks) row[i] = excl;
-      __syncthreads();
-      if (threadIdx.x == 1023) carry_sh = excl + v;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      const int total = (int)carry_sh;
-      if (c == 0) {
-        counts->n_keep = total;
-      } else {
-        counts->n_send[c - 1] = total;
-        if (total > mcap) st->mig_overflow = 1;
-        atomicMax(&st->max_send, (unsigned int)total);
-        float4* msg = (c == 1) ? send_l : send_r;
-        // an overflowing message is never packed (the batch is replayed): tell the receiver so
-        msg[0] = total > mcap ? hdr_fail() : hdr_make(total);
-      }
-    }
-    __syncthreads();
+  const int n = counts->n_own, L = counts->n_holes;
+  const int nl = counts->n_send[0], nr = counts->n_send[1];
+  const bool overflow = nl > mcap || nr > mcap;
+  if (threadIdx.x == 0) {
+    atomicMax(&st->max_send, (unsigned int)(nl > nr ? nl : nr));
+    if (overflow) st->mig_overflow = 1;
+    // an overflowing message is never complete (the batch is replayed): tell the receiver so
+    send_l[0] = overflow ? hdr_fail() : hdr_make(nl);
+    send_r[0] = overflow ? hdr_fail() : hdr_make(nr);
+    s_a = s_b = 0;
   }
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_slab_scatter(const float4* __restrict__ pos_o, const float4* __restrict__ pred_o, const uint32_t* __restrict__ gid_o,
-               const SlabCounts* __restrict__ counts, const uint32_t* __restrict__ blk_cnt, float4* __restrict__ keep_pos,
-               float4* __restrict__ keep_pred, float4* __restrict__ send_l, float4* __restrict__ send_r,
-               const StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int nblocks, int mcap) {
-  __shared__ uint32_t wc[3][kThreads / 32];
-  if (batch_failed(st)) return;
-  const int n = counts->n_own;
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
-  int cls = 3;
-  if (i < n) {
-    p = pos_o[i];
-    q = pred_o[i];
-    cls = slab_class(q.x, inv_h, cut_lo, cut_hi);
-  }
-  uint32_t rank_in_warp = 0;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
-    if (lane == 0) wc[c][warp] = __popc(m);
-    if (cls == c) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+  if (overflow) return;
+  __syncthreads();
+  const int base = n - L;  // owned particles that stay
+  uint32_t* list_a = holes + 2 * mcap;  // vacated slots below base
+  uint32_t* list_b = holes + 4 * mcap;  // stayers at or above base
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    const int h = (int)holes[t];
+    if (h < base) list_a[atomicAdd(&s_a, 1)] = (uint32_t)h;
+    const int i = base + t;
+    if (slab_class(pred_o[i].x, inv_h, cut_lo, cut_hi) == 0) list_b[atomicAdd(&s_b, 1)] = (uint32_t)i;
   }
   __syncthreads();
-  if (cls == 3) return;
-  uint32_t dst = blk_cnt[cls * nblocks + blockIdx.x] + rank_in_warp;
-  for (int w = 0; w < warp; ++w) dst += wc[cls][w];
-  p.w = __uint_as_float(gid_o[i]);
-  q.w = 0.0f;
-  if (cls == 0) {
-    keep_pos[dst] = p;
-    keep_pred[dst] = q;
-  } else if (dst < (uint32_t)mcap) {
-    float4* msg = (cls == 1) ? send_l : send_r;
-    msg[1 + dst] = p;
-    msg[1 + mcap + dst] = q;
+  const int moves = s_a;  // == s_b: L slots vanish, every stayer above base has a hole below it
+  for (int t = threadIdx.x; t < moves; t += blockDim.x) {
+    const uint32_t dst = list_a[t], src = list_b[t];
+    pos_o[dst] = pos_o[src];
+    pred_o[dst] = pred_o[src];
+    gid_o[dst] = gid_o[src];
   }
+  if (threadIdx.x == 0) counts->n_keep = base;
 }
 
-// ---------------------------------------------------------------- migration: merge
-__device__ __forceinline__ int lower_bound_gid(const float4* __restrict__ a, int n, uint32_t gid) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__float_as_uint(a[mid].w) < gid) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// Three sequences, each ascending in global id: kept (A), from the left (B), from the right (C).
-// Destination of an element = its index in its own sequence + the number of smaller ids in the
-// other two.  On the last hop the cell bounds of the merged set are taken for the grid.
+// Arrivals are appended after the particles that stayed.
 __global__ void __launch_bounds__(kThreads)
-k_slab_merge(const float4* __restrict__ keep_pos, const float4* __restrict__ keep_pred,
-             const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pos_o,
-             float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o, SlabCounts* __restrict__ counts,
-             StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int cap, int mcap, int last_hop) {
+k_slab_arrive(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pos_o,
+              float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o, SlabCounts* __restrict__ counts,
+              StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int cap, int mcap, int last_hop) {
   if (batch_failed(st)) return;
   if (hdr_failed(recv_l) || hdr_failed(recv_r)) {
     st->peer_failed = 1;
     return;
   }
-  const int nA = counts->n_keep;
+  const int base = counts->n_keep;
   const int nB = hdr_count(recv_l), nC = hdr_count(recv_r);
-  const int total = nA + nB + nC;
+  const int total = base + nB + nC;
   const int t = blockIdx.x * kThreads + threadIdx.x;
   if (t == 0) {
     atomicMax(&st->max_own, (unsigned int)total);
     if (total > cap) st->own_overflow = 1; else counts->n_own = total;
+    counts->n_send[0] = counts->n_send[1] = counts->n_holes = 0;  // for the next hop / substep
   }
   if (total > cap) return;
-  const float4* B = recv_l + 1;
-  const float4* C = recv_r + 1;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX};
   int hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-  if (t < total) {
-    float4 p, q;
-    int dst;
-    if (t < nA) {
-      p = keep_pos[t];
-      q = keep_pred[t];
-      dst = t;
-      if (nB | nC) {
-        const uint32_t gid = __float_as_uint(p.w);
-        dst += lower_bound_gid(B, nB, gid) + lower_bound_gid(C, nC, gid);
-      }
-    } else if (t - nA < nB) {
-      const int k = t - nA;
-      p = B[k];
-      q = B[mcap + k];
-      const uint32_t gid = __float_as_uint(p.w);
-      dst = k + lower_bound_gid(keep_pos, nA, gid) + lower_bound_gid(C, nC, gid);
-    } else {
-      const int k = t - nA - nB;
-      p = C[k];
-      q = C[mcap + k];
-      const uint32_t gid = __float_as_uint(p.w);
-      dst = k + lower_bound_gid(keep_pos, nA, gid) + lower_bound_gid(B, nB, gid);
-    }
+  if (t < nB + nC) {
+    const float4* msg = t < nB ? recv_l : recv_r;
+    const int k = t < nB ? t : t - nB;
+    const float4 p = msg[1 + k], q = msg[1 + mcap + k];
+    const int dst = base + t;
     gid_o[dst] = __float_as_uint(p.w);
     pos_o[dst] = make_float4(p.x, p.y, p.z, 0.0f);
     pred_o[dst] = make_float4(q.x, q.y, q.z, 0.0f);
-    if (last_hop) {
-      const int cx = cell_coord(q.x, inv_h), cy = cell_coord(q.y, inv_h), cz = cell_coord(q.z, inv_h);
-      lo[0] = hi[0] = cx;
-      lo[1] = hi[1] = cy;
-      lo[2] = hi[2] = cz;
-      if (cx < cut_lo || cx >= cut_hi) st->far_migrant = 1;  // needs another hop: the batch is replayed
-    }
+    const int cx = cell_coord(q.x, inv_h), cy = cell_coord(q.y, inv_h), cz = cell_coord(q.z, inv_h);
+    lo[0] = hi[0] = cx;
+    lo[1] = hi[1] = cy;
+    lo[2] = hi[2] = cz;
+    if (last_hop && (cx < cut_lo || cx >= cut_hi)) st->far_migrant = 1;  // needs another hop: the batch is replayed
   }
-  if (!last_hop) return;
-  // block-level reduction, then six pre-checked atomics per block (see k_predict)
-  __shared__ int s_lo[3][kThreads / 32], s_hi[3][kThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the bounds of the particles that were here before come from k_predict (a superset: it also saw
+  // the leavers); the arrivals of every hop extend them
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int wlo = __reduce_min_sync(0xffffffffu, lo[a]);
     const int whi = __reduce_max_sync(0xffffffffu, hi[a]);
-    if (lane == 0) {
-      s_lo[a][warp] = wlo;
-      s_hi[a][warp] = whi;
+    if ((threadIdx.x & 31) == 0 && wlo != INT_MAX) {
+      if (wlo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], wlo);
+      if (whi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], whi);
     }
-  }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    const int a = threadIdx.x;
-    int blo = INT_MAX, bhi = INT_MIN;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-      blo = min(blo, s_lo[a][w]);
-      bhi = max(bhi, s_hi[a][w]);
-    }
-    if (blo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], blo);
-    if (bhi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], bhi);
   }
 }
 
@@ -408,21 +304,19 @@ inline int grid_for(int n) { return (n + kThreads - 1) / kThreads; }
 }  // namespace
 
 // ================================================================== launchers
-int launch_slab_split(const float4* pos_o, const float4* pred_o, const SlabBuffers& sb, const StepConsts& c,
-                      cudaStream_t s) {
-  const int nb = grid_for(sb.cap);
-  k_slab_count<<<nb, kThreads, 0, s>>>(pred_o, sb.counts, sb.blk_cnt, sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, nb);
-  k_slab_scan<<<1, 1024, 0, s>>>(sb.blk_cnt, sb.counts, sb.status, sb.send[0], sb.send[1], nb, sb.mcap);
-  k_slab_scatter<<<nb, kThreads, 0, s>>>(pos_o, pred_o, sb.gid_o, sb.counts, sb.blk_cnt, sb.keep_pos, sb.keep_pred,
-                                         sb.send[0], sb.send[1], sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, nb, sb.mcap);
-  return 3;
+int launch_slab_split(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, cudaStream_t s) {
+  k_slab_leave<<<grid_for(sb.cap), kThreads, 0, s>>>(pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0],
+                                                    sb.send[1], sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, sb.mcap);
+  k_slab_refill<<<1, 1024, 0, s>>>(pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0], sb.send[1], sb.status,
+                                  c.inv_h, sb.cut_lo, sb.cut_hi, sb.mcap);
+  return 2;
 }
 
 int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, bool last_hop,
                       cudaStream_t s) {
-  k_slab_merge<<<grid_for(sb.cap + 2 * sb.mcap), kThreads, 0, s>>>(
-      sb.keep_pos, sb.keep_pred, sb.recv[0], sb.recv[1], pos_o, pred_o, sb.gid_o, sb.counts, sb.status, c.inv_h,
-      sb.cut_lo, sb.cut_hi, sb.cap, sb.mcap, last_hop ? 1 : 0);
+  k_slab_arrive<<<grid_for(2 * sb.mcap), kThreads, 0, s>>>(sb.recv[0], sb.recv[1], pos_o, pred_o, sb.gid_o, sb.counts,
+                                                          sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, sb.cap, sb.mcap,
+                                                          last_hop ? 1 : 0);
   return 1;
 }
 

@@ -91,12 +91,6 @@ StepConsts make_consts(const pbf_params& p, int nplanes) {
 
 namespace pbf {
 
-int sort_passes_for(uint32_t cell_cap) {
-  int bits = 1;
-  while (bits < 32 && (1ull << bits) < (unsigned long long)cell_cap) ++bits;
-  return (bits + kRadixBits - 1) / kRadixBits;
-}
-
 void invalidate_graph(pbf_ctx* ctx) {
   if (ctx->graph_exec) {
     cudaGraphExecDestroy(ctx->graph_exec);
@@ -129,16 +123,11 @@ int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep) {
   PBF_CUDA(ctx, ctx->keys1.reserve(cap));
   PBF_CUDA(ctx, ctx->vals0.reserve(cap));
   PBF_CUDA(ctx, ctx->vals1.reserve(cap));
-  PBF_CUDA(ctx, ctx->hist.reserve((size_t)kRadixBins * sort_blocks((int)cap)));
-  PBF_CUDA(ctx, ctx->chunk_total.reserve((size_t)kRadixBins * sort_blocks((int)cap) / 2048 + 2));
   PBF_CUDA(ctx, ctx->nbr_count.reserve(tot));
   for (auto& b : ctx->soa) PBF_CUDA(ctx, b.reserve(cap));
   if (ctx->slab.enabled) {
     PBF_CUDA(ctx, ctx->slab.gid_o.grow_keep(cap, keep));
     PBF_CUDA(ctx, ctx->slab.gid_bak.grow_keep(cap, keep));
-    PBF_CUDA(ctx, ctx->slab.keep_pos.reserve(cap));
-    PBF_CUDA(ctx, ctx->slab.keep_pred.reserve(cap));
-    PBF_CUDA(ctx, ctx->slab.blk_cnt.reserve(3 * ((cap + 255) / 256) + 3));
   }
   ctx->cap = cap;
   ctx->slab.tot_cap = ctx->slab.enabled ? tot : 0;
@@ -151,8 +140,7 @@ int ensure_tables(pbf_ctx* ctx) {
     PBF_CUDA(ctx, ctx->cell_range.reserve(ctx->cell_cap));
     PBF_CUDA(ctx, ctx->cell_count.reserve(ctx->cell_cap));
     PBF_CUDA(ctx, ctx->cell_excl.reserve(ctx->cell_cap));
-    // one chunk total per 2048 table cells (the radix scan needs far fewer)
-    PBF_CUDA(ctx, ctx->chunk_total.reserve(ctx->cell_cap / 2048 + 2 + (size_t)kRadixBins * sort_blocks((int)ctx->cap) / 2048));
+    PBF_CUDA(ctx, ctx->chunk_total.reserve(ctx->cell_cap / 2048 + 2));  // one chunk total per 2048 table cells
   }
   if (ctx->slot_id.n < ctx->cap) {
     invalidate_graph(ctx);
@@ -222,14 +210,12 @@ void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g) {
   g.keys[1] = ctx->keys1.p;
   g.vals[0] = ctx->vals0.p;
   g.vals[1] = ctx->vals1.p;
-  g.hist = ctx->hist.p;
   g.chunk_total = ctx->chunk_total.p;
   g.cell_range = ctx->cell_range.p;
   g.cell_count = ctx->cell_count.p;
   g.cell_excl = ctx->cell_excl.p;
   g.slot_id = ctx->slot_id.p;
   g.cell_cap = ctx->cell_cap;
-  g.sort_passes = sort_passes_for(ctx->cell_cap);
 }
 
 void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
@@ -276,7 +262,7 @@ int enqueue_substep(pbf_ctx* ctx) {
   ctx->sorted_buf = out;
 
   stage_mark(ctx, PBF_STAGE_CELLS, 1);
-  k = launch_cells_reorder(g.keys[out], g.vals[out], ctx->pred_o.p, ctx->pos_o.p, ctx->pred_a.p, ctx->pos_s.p, g, n, s);
+  k = launch_cells_reorder(ctx->pred_o.p, ctx->pos_o.p, ctx->pred_a.p, ctx->pos_s.p, nullptr, g, n, s);
   stage_mark(ctx, PBF_STAGE_CELLS, 0);
   t.launches[PBF_STAGE_CELLS] += k; launches += k;
 
@@ -445,7 +431,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->planes_dev.release(); ctx->desc.release(); ctx->status.release();
   ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
   ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release();
-  ctx->hist.release(); ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
+  ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
   ctx->dbg_dv.release(); ctx->dbg_eta.release();

@@ -92,8 +92,8 @@ struct SlabState {
   Transport* transport = nullptr;          // not owned when it belongs to a group
   bool owns_transport = false;
   DevBuf<SlabCounts> counts;
-  DevBuf<uint32_t> gid_o, gid_bak, blk_cnt;
-  DevBuf<float4> keep_pos, keep_pred;
+  DevBuf<uint32_t> gid_o, gid_bak;
+  DevBuf<uint32_t> holes;                  // 6 * mcap: slots vacated by migrants + two scratch lists
   DevBuf<float4> send[2][2], recv[2];      // [parity][side], [side]
   SlabCounts* counts_host = nullptr;       // pinned
   std::vector<uint32_t> gid_host;          // staging of global ids for upload / download
@@ -136,7 +136,7 @@ struct pbf_ctx {
   // grid
   pbf::DevBuf<pbf::GridDesc> desc;
   pbf::DevBuf<pbf::StatusBlock> status;
-  pbf::DevBuf<uint32_t> keys0, keys1, vals0, vals1, hist, chunk_total;
+  pbf::DevBuf<uint32_t> keys0, keys1, vals0, vals1, chunk_total;
   pbf::DevBuf<int2> cell_range;
   pbf::DevBuf<uint32_t> cell_count, cell_excl, slot_id;
   uint32_t cell_cap = 1u << 22;
@@ -176,7 +176,6 @@ struct pbf_ctx {
 
 namespace pbf {
 int fail(pbf_ctx* ctx, int code, const std::string& msg);
-int sort_passes_for(uint32_t cell_cap);
 void invalidate_graph(pbf_ctx* ctx);
 int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep);
 int ensure_tables(pbf_ctx* ctx);

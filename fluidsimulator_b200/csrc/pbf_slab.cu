@@ -382,6 +382,7 @@ int ensure_slab_buffers(pbf_ctx* ctx) {
     PBF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&sl.counts_host), sizeof(SlabCounts)));
     std::memset(sl.counts_host, 0, sizeof(SlabCounts));
   }
+  PBF_CUDA(ctx, sl.holes.reserve(6 * (size_t)sl.mcap + 64));
   const size_t elems = 1 + 2 * (size_t)std::max(sl.mcap, sl.gcap);
   if (elems > sl.msg_elems) {
     for (int p = 0; p < 2; ++p)
@@ -404,9 +405,7 @@ void slab_fill(pbf_ctx* ctx, SlabBuffers& sb) {
   sb.counts = sl.counts.p;
   sb.status = ctx->status.p;
   sb.gid_o = sl.gid_o.p;
-  sb.keep_pos = sl.keep_pos.p;
-  sb.keep_pred = sl.keep_pred.p;
-  sb.blk_cnt = sl.blk_cnt.p;
+  sb.holes = sl.holes.p;
   sb.send[0] = sb.send[1] = sb.recv[0] = sb.recv[1] = nullptr;  // slab_bind, per exchange
   sb.cut_lo = sl.cut_lo;
   sb.cut_hi = sl.cut_hi;
@@ -496,7 +495,7 @@ int slab_substep(pbf_ctx* ctx) {
   ctx->sorted_buf = out;
 
   stage_mark(ctx, PBF_STAGE_CELLS, 1);
-  k = launch_cells_reorder(g.keys[out], g.vals[out], ctx->pred_o.p, ctx->pos_o.p, ctx->pred_a.p, ctx->pos_s.p, g, n_own, s);
+  k = launch_cells_reorder(ctx->pred_o.p, ctx->pos_o.p, ctx->pred_a.p, ctx->pos_s.p, sl.gid_o.p, g, n_own, s);
   stage_mark(ctx, PBF_STAGE_CELLS, 0);
   t.launches[PBF_STAGE_CELLS] += k; launches += k;
 
@@ -598,8 +597,7 @@ void slab_release(pbf_ctx* ctx) {
   SlabState& sl = ctx->slab;
   if (sl.owns_transport && sl.transport) delete sl.transport;
   sl.transport = nullptr;
-  sl.counts.release(); sl.gid_o.release(); sl.gid_bak.release(); sl.blk_cnt.release();
-  sl.keep_pos.release(); sl.keep_pred.release();
+  sl.counts.release(); sl.gid_o.release(); sl.gid_bak.release(); sl.holes.release();
   for (int p = 0; p < 2; ++p)
     for (int side = 0; side < 2; ++side) sl.send[p][side].release();
   sl.recv[0].release(); sl.recv[1].release();
@@ -885,8 +883,8 @@ int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, cons
   std::vector<uint32_t>& gid = ctx->slab.gid_host;
   gid.resize(n);
   for (size_t i = 0; i < n; ++i) {
-    if (global_id[i] < 0 || global_id[i] > 0xfffffff0ll || (i > 0 && global_id[i] <= global_id[i - 1]))
-      return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: global ids must be ascending and unique");
+    if (global_id[i] < 0 || global_id[i] > 0xfffffff0ll)
+      return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: global id out of range");
     gid[i] = (uint32_t)global_id[i];
   }
   // A particle outside the cuts is legal input: the next substep migrates it (one hop per slab).

@@ -215,13 +215,14 @@ int pbf_slab_set_p2p(pbf_ctx* ctx, int enabled);
  * pbf_set_params) and keeps the particles of its slab; global ids = indices into these arrays. */
 int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float* py,
                     const float* pz, const float* vx, const float* vy, const float* vz);
-/* This rank's own particles only (ascending global ids, inside its cuts): the per-rank analogue
- * of pbf_upload.  The cuts of the last pbf_slab_upload stay. */
+/* This rank's own particles only (unique global ids, in any order): the per-rank analogue of
+ * pbf_upload.  The cuts of the last pbf_slab_upload stay; particles outside them migrate during
+ * the next substep. */
 int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, const float* px,
                           const float* py, const float* pz, const float* vx, const float* vy,
                           const float* vz);
 /* Particles currently owned by this slab (changes as particles migrate), its cuts, and the
- * owned particles with their global ids (ascending). */
+ * owned particles with their global ids (in the slab's storage order, which is arbitrary). */
 size_t pbf_slab_owned(const pbf_ctx* ctx);
 int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi);
 /* Re-balancing: new cuts for this slab (e.g. from pbf_slab_plan on the gathered positions).  By
