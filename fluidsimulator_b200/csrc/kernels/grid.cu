@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(kThreads)
 k_pack_state(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
              const float* __restrict__ vx, const float* __restrict__ vy, const float* __restrict__ vz,
              float4* __restrict__ pos_o, float4* __restrict__ vel_o, int n) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   pos_o[i] = make_float4(px[i], py[i], pz[i], 0.0f);
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(kThreads)
 k_unpack_state(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
                float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz,
                float* __restrict__ vx, float* __restrict__ vy, float* __restrict__ vz, int n) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = pos_o[i];
@@ -58,6 +60,7 @@ k_unpack_state(const float4* __restrict__ pos_o, const float4* __restrict__ vel_
 __global__ void __launch_bounds__(kThreads)
 k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
           float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, NRef nr, int do_bounds) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX};
@@ -109,6 +112,7 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
 // `pad` empty layers surround the occupied cells: 1 so the 27-cell stencil of every particle stays
 // inside the table; 2 in slab mode, where first-layer ghosts run their own stencil.
 __global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad) {
+  pdl_wait();
   if (batch_failed(st)) return;
   unsigned long long cells = 1;
   bool bad = false;
@@ -157,6 +161,7 @@ constexpr int kScanChunk = kScanThreads * kScanItems;  // 2048 entries per block
 // Exclusive scan of the chunk totals, in place (one block; there are m / kScanChunk of them).
 __global__ void __launch_bounds__(1024)
 k_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nchunks) {
+  pdl_wait();
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_sh;
   if (batch_failed(st)) return;
@@ -207,6 +212,7 @@ __global__ void __launch_bounds__(kThreads)
 k_cell_count(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ arrival,
              uint32_t* __restrict__ cell_count, float inv_h, const GridDesc* __restrict__ desc,
              const StatusBlock* st, NRef nr) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,6 +226,7 @@ k_cell_count(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uin
 __global__ void __launch_bounds__(kScanThreads)
 k_cell_scan(const uint32_t* __restrict__ cell_count, uint32_t* __restrict__ cell_excl,
             uint32_t* __restrict__ chunk_total, const GridDesc* __restrict__ desc, const StatusBlock* st) {
+  pdl_wait();
   __shared__ uint32_t warp_sums[kScanThreads / 32];
   if (batch_failed(st)) return;
   const int m = (int)desc->ncells;
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(kThreads)
 k_cell_ranges(uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ cell_excl,
               const uint32_t* __restrict__ chunk_total, int2* __restrict__ cell_range,
               const GridDesc* __restrict__ desc, const StatusBlock* st) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const uint32_t ncells = desc->ncells;
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
@@ -278,6 +286,7 @@ k_cell_ranges(uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ ce
 __global__ void __launch_bounds__(kThreads)
 k_cell_place(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ arrival,
              const int2* __restrict__ cell_range, uint32_t* __restrict__ slot_id, const StatusBlock* st, NRef nr) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,6 +301,7 @@ k_cell_order(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slo
              const float4* __restrict__ pos_o, uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ vals_sorted,
              float4* __restrict__ pred_s, float4* __restrict__ pos_s, const uint32_t* __restrict__ gid,
              const StatusBlock* st, NRef nr) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,6 +378,7 @@ __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
             const GridDesc* __restrict__ desc, uint32_t* __restrict__ nbr_idx,
             uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2, int K, NRef nr) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -427,14 +438,14 @@ inline int grid_for(int n, int threads) { return (n + threads - 1) / threads; }
 // ================================================================== launchers
 int launch_pack_state(const float* const soa[6], float4* pos_o, float4* vel_o, int n, cudaStream_t s) {
   if (n <= 0) return 0;
-  k_pack_state<<<grid_for(n, kThreads), kThreads, 0, s>>>(soa[0], soa[1], soa[2], soa[3], soa[4], soa[5],
+  PBF_LAUNCH(k_pack_state, grid_for(n, kThreads), kThreads, s, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5],
                                                          pos_o, vel_o, n);
   return 1;
 }
 
 int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const soa[6], int n, cudaStream_t s) {
   if (n <= 0) return 0;
-  k_unpack_state<<<grid_for(n, kThreads), kThreads, 0, s>>>(pos_o, vel_o, soa[0], soa[1], soa[2], soa[3],
+  PBF_LAUNCH(k_unpack_state, grid_for(n, kThreads), kThreads, s, pos_o, vel_o, soa[0], soa[1], soa[2], soa[3],
                                                            soa[4], soa[5], n);
   return 1;
 }
@@ -445,14 +456,14 @@ int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConst
   // stream at HBM speed, few enough warps that the six bound atomics stay cheap
   int blocks = grid_for(n.n, kThreads);
   if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
-  k_predict<<<blocks, kThreads, 0, s>>>(pos_o, vel_o, pred_o, c, g.status, n, 1);
+  PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1);
   if (slab) return 1;  // migrants extend the bounds; the table descriptor follows (launch_grid_finalize)
-  k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap, 1);
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1);
   return 2;
 }
 
 int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s) {
-  k_grid_finalize<<<1, 1, 0, s>>>(g.desc, g.status, g.cell_cap, pad);
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, pad);
   return 1;
 }
 
@@ -460,14 +471,14 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
                 cudaStream_t s) {
   // keys[0] = key per particle, vals[0] = arrival slot inside its cell; the ordered result
   // (keys[1], vals[1]) is written by launch_cells_reorder
-  k_cell_count<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(pred_o, g.keys[0], g.vals[0], g.cell_count, c.inv_h,
+  PBF_LAUNCH(k_cell_count, grid_for(n.n, kThreads), kThreads, s, pred_o, g.keys[0], g.vals[0], g.cell_count, c.inv_h,
                                                            g.desc, g.status, n);
   const int nchunks = (int)((g.cell_cap + kScanChunk - 1) / kScanChunk);
-  k_cell_scan<<<nchunks, kScanThreads, 0, s>>>(g.cell_count, g.cell_excl, g.chunk_total, g.desc, g.status);
-  k_scan_chunks<<<1, 1024, 0, s>>>(g.chunk_total, g.status, nchunks);
-  k_cell_ranges<<<148 * 8, kThreads, 0, s>>>(g.cell_count, g.cell_excl, g.chunk_total, g.cell_range, g.desc,
+  PBF_LAUNCH(k_cell_scan, nchunks, kScanThreads, s, g.cell_count, g.cell_excl, g.chunk_total, g.desc, g.status);
+  PBF_LAUNCH(k_scan_chunks, 1, 1024, s, g.chunk_total, g.status, nchunks);
+  PBF_LAUNCH(k_cell_ranges, 148 * 8, kThreads, s, g.cell_count, g.cell_excl, g.chunk_total, g.cell_range, g.desc,
                                             g.status);
-  k_cell_place<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(g.keys[0], g.vals[0], g.cell_range, g.slot_id,
+  PBF_LAUNCH(k_cell_place, grid_for(n.n, kThreads), kThreads, s, g.keys[0], g.vals[0], g.cell_range, g.slot_id,
                                                            g.status, n);
   *out = 1;
   return 5;
@@ -475,14 +486,14 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
 
 int launch_cells_reorder(const float4* pred_o, const float4* pos_o, float4* pred_s, float4* pos_s,
                          const uint32_t* gid, const GridBuffers& g, NRef n, cudaStream_t s) {
-  k_cell_order<<<grid_for(n.n, kThreads), kThreads, 0, s>>>(g.keys[0], g.slot_id, g.cell_range, pred_o, pos_o,
+  PBF_LAUNCH(k_cell_order, grid_for(n.n, kThreads), kThreads, s, g.keys[0], g.slot_id, g.cell_range, pred_o, pos_o,
                                                            g.keys[1], g.vals[1], pred_s, pos_s, gid, g.status, n);
   return 1;
 }
 
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,
                      const NeighborList& nl, NRef n, cudaStream_t s) {
-  k_neighbors<<<grid_for(n.n, 128), 128, 0, s>>>(pred_s, g.cell_range, g.desc, nl.idx, nl.count, g.status,
+  PBF_LAUNCH(k_neighbors, grid_for(n.n, 128), 128, s, pred_s, g.cell_range, g.desc, nl.idx, nl.count, g.status,
                                                 c.inv_h, c.h2, nl.K, n);
   return 1;
 }

@@ -10,6 +10,24 @@
 
 namespace pbf {
 
+// <<<grid, block, 0, stream>>> with programmatic stream serialization (see pdl_wait in pbf_device.cuh)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = PBF_PDL ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define PBF_LAUNCH(kernel, grid, block, stream, ...) \
+  ::pbf::launch_pdl(kernel, dim3(grid), dim3(block), stream, __VA_ARGS__)
+
 struct GridBuffers {
   GridDesc* desc;
   StatusBlock* status;

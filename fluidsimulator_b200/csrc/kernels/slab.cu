@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kThreads)
 k_slab_leave(const float4* __restrict__ pos_o, const float4* __restrict__ pred_o, const uint32_t* __restrict__ gid_o,
              SlabCounts* __restrict__ counts, uint32_t* __restrict__ holes, float4* __restrict__ send_l,
              float4* __restrict__ send_r, const StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int mcap) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= counts->n_own) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(1024)
 k_slab_refill(float4* __restrict__ pos_o, float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o,
               SlabCounts* __restrict__ counts, uint32_t* __restrict__ holes, float4* send_l, float4* send_r,
               StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int mcap) {
+  pdl_wait();
   __shared__ int s_a, s_b;
   if (batch_failed(st)) {
     if (threadIdx.x == 0) send_l[0] = send_r[0] = hdr_fail();
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(kThreads)
 k_slab_arrive(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pos_o,
               float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o, SlabCounts* __restrict__ counts,
               StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int cap, int mcap, int last_hop) {
+  pdl_wait();
   if (batch_failed(st)) return;
   if (hdr_failed(recv_l) || hdr_failed(recv_r)) {
     st->peer_failed = 1;
@@ -164,6 +167,7 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys
 __global__ void k_slab_bounds(const uint32_t* __restrict__ keys, const GridDesc* __restrict__ desc,
                               SlabCounts* __restrict__ counts, StatusBlock* st, float4* send_l, float4* send_r,
                               int cut_lo, int cut_hi, int gcap) {
+  pdl_wait();
   if (batch_failed(st)) {
     send_l[0] = send_r[0] = hdr_fail();
     return;
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(kThreads)
 k_slab_ghost_pack(const float4* __restrict__ pred_s, const float4* __restrict__ pos_s,
                   const SlabCounts* __restrict__ counts, float4* __restrict__ send_l, float4* __restrict__ send_r,
                   const StatusBlock* st, int gcap) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int t = blockIdx.x * kThreads + threadIdx.x;
   const int side = t / gcap, k = t - side * gcap;
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(kThreads)
 k_slab_ghost_unpack(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pred_s,
                     float4* __restrict__ pos_s, int2* __restrict__ cell_range, const GridDesc* __restrict__ desc,
                     SlabCounts* __restrict__ counts, StatusBlock* st, float inv_h, int gcap, int tot_cap) {
+  pdl_wait();
   if (batch_failed(st)) return;
   if (hdr_failed(recv_l) || hdr_failed(recv_r)) {
     st->peer_failed = 1;
@@ -264,6 +270,7 @@ k_slab_ghost_unpack(const float4* __restrict__ recv_l, const float4* __restrict_
 __global__ void __launch_bounds__(kThreads)
 k_slab_halo_unpack(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ arr,
                    const SlabCounts* __restrict__ counts, const StatusBlock* st, int gcap) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int t = blockIdx.x * kThreads + threadIdx.x;
   const int side = t / gcap, k = t - side * gcap;
@@ -278,6 +285,7 @@ template <bool S>
 __global__ void __launch_bounds__(kThreads)
 k_slab_ghost_vel(const float4* __restrict__ pred, const float4* __restrict__ pos_s, const float* __restrict__ rho,
                  float4* __restrict__ vel, const SlabCounts* __restrict__ counts, const StatusBlock* st, StepConsts c) {
+  pdl_wait();
   if (batch_failed(st)) return;
   const int i = counts->n_own + blockIdx.x * kThreads + threadIdx.x;
   if (i >= counts->n_tot) return;
@@ -305,16 +313,16 @@ inline int grid_for(int n) { return (n + kThreads - 1) / kThreads; }
 
 // ================================================================== launchers
 int launch_slab_split(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, cudaStream_t s) {
-  k_slab_leave<<<grid_for(sb.cap), kThreads, 0, s>>>(pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0],
+  PBF_LAUNCH(k_slab_leave, grid_for(sb.cap), kThreads, s, pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0],
                                                     sb.send[1], sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, sb.mcap);
-  k_slab_refill<<<1, 1024, 0, s>>>(pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0], sb.send[1], sb.status,
+  PBF_LAUNCH(k_slab_refill, 1, 1024, s, pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0], sb.send[1], sb.status,
                                   c.inv_h, sb.cut_lo, sb.cut_hi, sb.mcap);
   return 2;
 }
 
 int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, bool last_hop,
                       cudaStream_t s) {
-  k_slab_arrive<<<grid_for(2 * sb.mcap), kThreads, 0, s>>>(sb.recv[0], sb.recv[1], pos_o, pred_o, sb.gid_o, sb.counts,
+  PBF_LAUNCH(k_slab_arrive, grid_for(2 * sb.mcap), kThreads, s, sb.recv[0], sb.recv[1], pos_o, pred_o, sb.gid_o, sb.counts,
                                                           sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, sb.cap, sb.mcap,
                                                           last_hop ? 1 : 0);
   return 1;
@@ -322,23 +330,23 @@ int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, cons
 
 int launch_slab_ghost_pack(const uint32_t* keys_sorted, const float4* pred_s, const float4* pos_s,
                            const GridBuffers& g, const SlabBuffers& sb, cudaStream_t s) {
-  k_slab_bounds<<<1, 1, 0, s>>>(keys_sorted, g.desc, sb.counts, sb.status, sb.send[0], sb.send[1], sb.cut_lo,
+  PBF_LAUNCH(k_slab_bounds, 1, 1, s, keys_sorted, g.desc, sb.counts, sb.status, sb.send[0], sb.send[1], sb.cut_lo,
                                sb.cut_hi, sb.gcap);
-  k_slab_ghost_pack<<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(pred_s, pos_s, sb.counts, sb.send[0], sb.send[1],
+  PBF_LAUNCH(k_slab_ghost_pack, grid_for(2 * sb.gcap), kThreads, s, pred_s, pos_s, sb.counts, sb.send[0], sb.send[1],
                                                               sb.status, sb.gcap);
   return 2;
 }
 
 int launch_slab_ghost_unpack(float4* pred_s, float4* pos_s, const GridBuffers& g, const SlabBuffers& sb,
                              const StepConsts& c, cudaStream_t s) {
-  k_slab_ghost_unpack<<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(sb.recv[0], sb.recv[1], pred_s, pos_s, g.cell_range,
+  PBF_LAUNCH(k_slab_ghost_unpack, grid_for(2 * sb.gcap), kThreads, s, sb.recv[0], sb.recv[1], pred_s, pos_s, g.cell_range,
                                                                 g.desc, sb.counts, sb.status, c.inv_h, sb.gcap,
                                                                 sb.tot_cap);
   return 1;
 }
 
 int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s) {
-  k_slab_halo_unpack<<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(sb.recv[0], sb.recv[1], arr, sb.counts, sb.status,
+  PBF_LAUNCH(k_slab_halo_unpack, grid_for(2 * sb.gcap), kThreads, s, sb.recv[0], sb.recv[1], arr, sb.counts, sb.status,
                                                                sb.gcap);
   return 1;
 }
@@ -346,9 +354,9 @@ int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s) 
 int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel,
                           const SlabBuffers& sb, const StepConsts& c, bool strict, cudaStream_t s) {
   if (strict)
-    k_slab_ghost_vel<true><<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(pred_final, pos_s, rho, vel, sb.counts, sb.status, c);
+    PBF_LAUNCH(k_slab_ghost_vel<true>, grid_for(2 * sb.gcap), kThreads, s, pred_final, pos_s, rho, vel, sb.counts, sb.status, c);
   else
-    k_slab_ghost_vel<false><<<grid_for(2 * sb.gcap), kThreads, 0, s>>>(pred_final, pos_s, rho, vel, sb.counts, sb.status, c);
+    PBF_LAUNCH(k_slab_ghost_vel<false>, grid_for(2 * sb.gcap), kThreads, s, pred_final, pos_s, rho, vel, sb.counts, sb.status, c);
   return 1;
 }
 

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
          const StatusBlock* st, DebugPtrs dbg, int K, NRef nr) {
+  pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
@@ -354,6 +355,7 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const float4* __restrict__ pos_s, const float* __restrict__ rho, float4* __restrict__ vel_out,
         const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
         StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final, int K, NRef nr) {
+  pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
@@ -438,6 +440,7 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
        const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
        float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final,
        int K, NRef nr) {
+  pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
@@ -485,6 +488,7 @@ __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* __restrict__ omega,
              const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count, StepConsts c,
              const StatusBlock* st, int K, NRef nr) {
+  pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
@@ -532,6 +536,7 @@ k_vort_apply(const float4* __restrict__ pos, const float4* __restrict__ vel, con
              const float4* __restrict__ pos_s, const float4* __restrict__ planes,
              float4* __restrict__ pos_o, float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st,
              DebugPtrs dbg, int K, NRef nr) {
+  pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
@@ -589,6 +594,7 @@ __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
               const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
               StepConsts c, const StatusBlock* st, NRef nr) {
+  pdl_wait();
   using F = FT<S>;
   if (batch_failed(st)) return;
   const int n = nr.get();
@@ -611,9 +617,9 @@ static inline int blocks_for(NRef n) { return (n.n + kBlock - 1) / kBlock; }
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
                   bool strict, cudaStream_t s) {
   if (strict)
-    k_lambda<true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+    PBF_LAUNCH(k_lambda<true>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
   else
-    k_lambda<false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+    PBF_LAUNCH(k_lambda<false>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
   return 1;
 }
 
@@ -621,11 +627,11 @@ template <bool S>
 static void delta_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
                        bool is_final, NRef n, cudaStream_t s) {
   if (last)
-    k_delta<S, true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
+    PBF_LAUNCH((k_delta<S, true>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
                                                      b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo,
                                                      is_final ? 1 : 0, nl.K, n);
   else
-    k_delta<S, false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
+    PBF_LAUNCH((k_delta<S, false>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
                                                       b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo, 0,
                                                       nl.K, n);
 }
@@ -640,10 +646,10 @@ int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts
 int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,
                 NRef n, bool strict, cudaStream_t s) {
   if (strict)
-    k_xsph<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
+    PBF_LAUNCH(k_xsph<true>, blocks_for(n), kBlock, s, pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
                                                  b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   else
-    k_xsph<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
+    PBF_LAUNCH(k_xsph<false>, blocks_for(n), kBlock, s, pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
                                                   b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   return 1;
 }
@@ -651,19 +657,19 @@ int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts&
 int launch_vort_omega(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
                       NRef n, bool strict, cudaStream_t s) {
   if (strict)
-    k_vort_omega<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
+    PBF_LAUNCH(k_vort_omega<true>, blocks_for(n), kBlock, s, pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
   else
-    k_vort_omega<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
+    PBF_LAUNCH(k_vort_omega<false>, blocks_for(n), kBlock, s, pos, b.vel[vcur], b.omega, nl.idx, nl.count, c, b.status, nl.K, n);
   return 1;
 }
 
 int launch_vort_apply(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
                       NRef n, bool strict, cudaStream_t s) {
   if (strict)
-    k_vort_apply<true><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
+    PBF_LAUNCH(k_vort_apply<true>, blocks_for(n), kBlock, s, pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
                                                        b.pos_o, b.vel_o, c, b.status, b.dbg, nl.K, n);
   else
-    k_vort_apply<false><<<blocks_for(n), kBlock, 0, s>>>(pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
+    PBF_LAUNCH(k_vort_apply<false>, blocks_for(n), kBlock, s, pos, b.vel[vcur], b.omega, nl.idx, nl.count, b.pos_s, b.planes,
                                                         b.pos_o, b.vel_o, c, b.status, b.dbg, nl.K, n);
   return 1;
 }
@@ -675,9 +681,9 @@ int launch_commit_only(const SolveBuffers& b, const StepConsts& c, NRef n, bool 
   c0.do_xsph = 0;
   c0.do_vort = 0;
   if (strict)
-    k_commit_only<true><<<blocks_for(n), kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
+    PBF_LAUNCH(k_commit_only<true>, blocks_for(n), kBlock, s, b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
   else
-    k_commit_only<false><<<blocks_for(n), kBlock, 0, s>>>(b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
+    PBF_LAUNCH(k_commit_only<false>, blocks_for(n), kBlock, s, b.pred[0], b.pos_s, b.planes, b.pos_o, b.vel_o, c0, b.status, n);
   return 1;
 }
 

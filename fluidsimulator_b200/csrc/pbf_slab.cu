@@ -219,6 +219,7 @@ constexpr size_t kMailboxElems = 16;  // float4 elements reserved for the mailbo
 
 __global__ void k_peer_signal_wait(PeerMailbox* mine, PeerMailbox* left, PeerMailbox* right, StatusBlock* st,
                                    long long timeout_cycles) {
+  pdl_wait();
   // All stores of the preceding pack kernel are complete (kernel boundary); the fences order them
   // before the flags at system scope.  Runs even when the batch has failed: a neighbour must never
   // be left waiting.
@@ -360,7 +361,7 @@ struct PeerTransport : Transport {
   int exchange(pbf_ctx* ctx, float4* const send[2], float4* const recv[2], size_t bytes) override {
     if (!active) return inner->exchange(ctx, send, recv, bytes);
     PeerMailbox* mine = reinterpret_cast<PeerMailbox*>(win);
-    k_peer_signal_wait<<<1, 1, 0, ctx->stream>>>(mine, reinterpret_cast<PeerMailbox*>(remote[0]),
+    PBF_LAUNCH(k_peer_signal_wait, 1, 1, ctx->stream, mine, reinterpret_cast<PeerMailbox*>(remote[0]),
                                                  reinterpret_cast<PeerMailbox*>(remote[1]), ctx->status.p,
                                                  4000000000LL);
     return PBF_OK;
