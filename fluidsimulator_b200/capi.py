@@ -138,6 +138,8 @@ ABI = {
     "pbf_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
     "pbf_download": (C.c_int, [C.c_void_p] + [_f32p] * 6),
     "pbf_step": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pbf_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pbf_step_host": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6 + [C.c_int]),
     "pbf_count": (C.c_size_t, [C.c_void_p]),
     "pbf_time": (C.c_float, [C.c_void_p]),

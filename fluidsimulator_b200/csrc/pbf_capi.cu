@@ -592,6 +592,21 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
   return fail(ctx, PBF_E_CAPACITY, "pbf_step: device tables kept overflowing after 32 growth attempts");
 }
 
+int pbf_host_register(pbf_ctx* ctx, void* ptr, size_t bytes) {
+  if (!ctx || !ptr || bytes == 0) return fail(ctx, PBF_E_INVALID, "pbf_host_register: bad arguments");
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return PBF_OK;
+}
+
+int pbf_host_unregister(pbf_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return fail(ctx, PBF_E_INVALID, "pbf_host_unregister: bad arguments");
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PBF_CUDA(ctx, cudaHostUnregister(ptr));
+  return PBF_OK;
+}
+
 int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz, int nsteps) {
   int rc = pbf_upload(ctx, n, px, py, pz, vx, vy, vz);
   if (rc != PBF_OK) return rc;

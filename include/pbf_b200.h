@@ -121,6 +121,13 @@ int pbf_download(pbf_ctx* ctx, float* px, float* py, float* pz, float* vx,
  * independent of table sizes). */
 int pbf_step(pbf_ctx* ctx, int nsteps);
 
+/* Page-locks (or releases) a caller-owned host array so that pbf_upload / pbf_download /
+ * pbf_step_host move it at full PCIe speed instead of through the driver's staging buffers.
+ * For callers whose arrays persist across steps, like fluid::State's std::vectors (the shim
+ * registers them once and re-registers when a vector is re-allocated).  Not required. */
+int pbf_host_register(pbf_ctx* ctx, void* ptr, size_t bytes);
+int pbf_host_unregister(pbf_ctx* ctx, void* ptr);
+
 /* The reference's cuda_step contract in one call (cuda_stub.cu:764-1099): host
  * arrays in, `nsteps` substeps, host arrays out, all inside the call. */
 int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz,
