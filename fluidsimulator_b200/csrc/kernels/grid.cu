@@ -59,10 +59,16 @@ k_unpack_state(const float4* __restrict__ pos_o, const float4* __restrict__ vel_
 // coordinates.  Grid-stride so that only a few thousand warps touch the six atomics.
 __global__ void __launch_bounds__(kThreads)
 k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
-          float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, NRef nr, int do_bounds) {
+          float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, NRef nr, int do_bounds,
+          const GridDesc* __restrict__ desc, unsigned long long* __restrict__ cell_key) {
   pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
+  // the sparse cell table of the PREVIOUS substep (if it was sparse) is wiped here, by the first
+  // kernel of the substep, so that the dense path never pays for it
+  if (desc->sparse)
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < desc->ncells; c += gridDim.x * blockDim.x)
+      cell_key[c] = kEmptyCell;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX};
   int hi[3] = {INT_MIN, INT_MIN, INT_MIN};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -111,7 +117,11 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
 
 // `pad` empty layers surround the occupied cells: 1 so the 27-cell stencil of every particle stays
 // inside the table; 2 in slab mode, where first-layer ghosts run their own stencil.
-__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad) {
+// When the box would need more cells than the table holds — the reference diverges with vorticity
+// on, SURVEY §0 — the substep switches to a SPARSE table: the same arrays, indexed by a hash of
+// the packed cell coordinates (`allow_sparse`; not in slab mode, whose ghost layers rely on the
+// x-major order of the dense key).
+__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad, NRef nr, int allow_sparse) {
   pdl_wait();
   if (batch_failed(st)) return;
   unsigned long long cells = 1;
@@ -134,23 +144,56 @@ __global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_c
     st->max_cell[a] = INT_MIN;
   }
   if (bad) cells = 0xffffffffffffULL;
+  // sparse alternative: a hash table at load factor <= 1/2 over cell_cap (a power of two) slots
+  const unsigned long long n = (unsigned long long)nr.get();
+  const bool packable = allow_sparse && !bad && desc->dim[0] < (1 << 21) && desc->dim[1] < (1 << 21) && desc->dim[2] < (1 << 21);
+  const bool dense = cells <= (unsigned long long)cell_cap;
+  const bool sparse = !dense && packable && 2 * n <= (unsigned long long)cell_cap;
+  // what the host must provide if neither fits: the smaller of the two tables
+  unsigned long long need = cells;
+  if (!dense && packable && 2 * n < need) need = 2 * n;
   const unsigned long long seen = ((unsigned long long)st->max_cells_hi << 32) | st->max_cells_lo;
-  if (cells > seen) {
-    st->max_cells_hi = (unsigned int)(cells >> 32);
-    st->max_cells_lo = (unsigned int)cells;
+  if (need > seen) {
+    st->max_cells_hi = (unsigned int)(need >> 32);
+    st->max_cells_lo = (unsigned int)need;
   }
-  const int overflow = (cells > (unsigned long long)cell_cap) ? 1 : 0;
-  desc->ncells = overflow ? 0u : (uint32_t)cells;
+  const int overflow = (dense || sparse) ? 0 : 1;
+  desc->ncells = overflow ? 0u : (dense ? (uint32_t)cells : cell_cap);
+  desc->sparse = sparse ? 1 : 0;
   desc->overflow = overflow;
   if (overflow) st->grid_overflow = 1;
 }
 
-// ---------------------------------------------------------------- a4/a5 keys + radix sort
+// ---------------------------------------------------------------- a4 cell keys
 __device__ __forceinline__ uint32_t dense_key(float4 q, float inv_h, const GridDesc& d) {
   const int cx = cell_coord(q.x, inv_h) - d.lo[0];
   const int cy = cell_coord(q.y, inv_h) - d.lo[1];
   const int cz = cell_coord(q.z, inv_h) - d.lo[2];
   return ((uint32_t)cx * (uint32_t)d.dim[1] + (uint32_t)cy) * (uint32_t)d.dim[2] + (uint32_t)cz;
+}
+
+// sparse table: slot of a cell, inserting it if new (linear probing; load factor <= 1/2)
+__device__ __forceinline__ uint32_t sparse_insert(unsigned long long* __restrict__ cell_key, uint32_t mask,
+                                                  unsigned long long key) {
+  uint32_t slot = hash_cell(key) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&cell_key[slot], kEmptyCell, key);
+    if (prev == kEmptyCell || prev == key) return slot;
+    slot = (slot + 1) & mask;
+  }
+}
+
+// (start, end) of the cell at bbox-relative coordinates (rx, ry, rz); empty if the cell does not exist
+__device__ __forceinline__ int2 sparse_lookup(const unsigned long long* __restrict__ cell_key,
+                                              const int2* __restrict__ cell_range, uint32_t mask, int rx, int ry, int rz) {
+  const unsigned long long key = pack_cell(rx, ry, rz);
+  uint32_t slot = hash_cell(key) & mask;
+  for (;;) {
+    const unsigned long long k = cell_key[slot];
+    if (k == key) return cell_range[slot];
+    if (k == kEmptyCell) return make_int2(0, 0);
+    slot = (slot + 1) & mask;
+  }
 }
 
 // Two-level exclusive scan helpers: a block scans one chunk of kScanChunk entries and publishes
@@ -211,13 +254,21 @@ k_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nch
 __global__ void __launch_bounds__(kThreads)
 k_cell_count(const float4* __restrict__ pred_o, uint32_t* __restrict__ keys, uint32_t* __restrict__ arrival,
              uint32_t* __restrict__ cell_count, float inv_h, const GridDesc* __restrict__ desc,
-             const StatusBlock* st, NRef nr) {
+             unsigned long long* __restrict__ cell_key, const StatusBlock* st, NRef nr) {
   pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t k = dense_key(pred_o[i], inv_h, *desc);
+  uint32_t k;
+  if (desc->sparse) {
+    const float4 q = pred_o[i];
+    k = sparse_insert(cell_key, desc->ncells - 1u,
+                      pack_cell((long long)cell_coord(q.x, inv_h) - desc->lo[0], (long long)cell_coord(q.y, inv_h) - desc->lo[1],
+                                (long long)cell_coord(q.z, inv_h) - desc->lo[2]));
+  } else {
+    k = dense_key(pred_o[i], inv_h, *desc);
+  }
   keys[i] = k;
   arrival[i] = atomicAdd(&cell_count[k], 1u);
 }
@@ -376,8 +427,9 @@ __device__ __forceinline__ void neighbors_cell(const float4* __restrict__ pred_s
 
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
-            const GridDesc* __restrict__ desc, uint32_t* __restrict__ nbr_idx,
-            uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2, int K, NRef nr) {
+            const GridDesc* __restrict__ desc, const unsigned long long* __restrict__ cell_key,
+            uint32_t* __restrict__ nbr_idx, uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2,
+            int K, NRef nr) {
   pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
@@ -405,14 +457,25 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
     e.off = 0;
     e.K = (uint32_t)K;
     const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
+    const bool sparse = desc->sparse != 0;
+    const uint32_t mask = desc->ncells - 1u;
     const f2 pxy = make_float2(pi.x, pi.y);
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll 1
       for (int dy = -1; dy <= 1; ++dy) {
-        const uint32_t row = ((uint32_t)(cx - 1) * (uint32_t)dimy + (uint32_t)(cy + dy)) * (uint32_t)dimz +
-                             (uint32_t)(cz + dz);
-        const int2 r0 = cell_range[row], r1 = cell_range[row + xstride], r2 = cell_range[row + 2u * xstride];
+        int2 r0, r1, r2;
+        if (sparse) {
+          r0 = sparse_lookup(cell_key, cell_range, mask, cx - 1, cy + dy, cz + dz);
+          r1 = sparse_lookup(cell_key, cell_range, mask, cx, cy + dy, cz + dz);
+          r2 = sparse_lookup(cell_key, cell_range, mask, cx + 1, cy + dy, cz + dz);
+        } else {
+          const uint32_t row = ((uint32_t)(cx - 1) * (uint32_t)dimy + (uint32_t)(cy + dy)) * (uint32_t)dimz +
+                               (uint32_t)(cz + dz);
+          r0 = cell_range[row];
+          r1 = cell_range[row + xstride];
+          r2 = cell_range[row + 2u * xstride];
+        }
         neighbors_cell<false>(pred_s, r0, pi, pxy, i, h2, e);
         if (dz == 0 && dy == 0)
           neighbors_cell<true>(pred_s, r1, pi, pxy, i, h2, e);
@@ -456,14 +519,14 @@ int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConst
   // stream at HBM speed, few enough warps that the six bound atomics stay cheap
   int blocks = grid_for(n.n, kThreads);
   if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
-  PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1);
+  PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1, g.desc, g.cell_key);
   if (slab) return 1;  // migrants extend the bounds; the table descriptor follows (launch_grid_finalize)
-  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1);
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1, n, 1);
   return 2;
 }
 
-int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s) {
-  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, pad);
+int launch_grid_finalize(const GridBuffers& g, int pad, NRef n, cudaStream_t s) {
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, pad, n, 0);
   return 1;
 }
 
@@ -472,7 +535,7 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
   // keys[0] = key per particle, vals[0] = arrival slot inside its cell; the ordered result
   // (keys[1], vals[1]) is written by launch_cells_reorder
   PBF_LAUNCH(k_cell_count, grid_for(n.n, kThreads), kThreads, s, pred_o, g.keys[0], g.vals[0], g.cell_count, c.inv_h,
-                                                           g.desc, g.status, n);
+             g.desc, g.cell_key, g.status, n);
   const int nchunks = (int)((g.cell_cap + kScanChunk - 1) / kScanChunk);
   PBF_LAUNCH(k_cell_scan, nchunks, kScanThreads, s, g.cell_count, g.cell_excl, g.chunk_total, g.desc, g.status);
   PBF_LAUNCH(k_scan_chunks, 1, 1024, s, g.chunk_total, g.status, nchunks);
@@ -493,8 +556,8 @@ int launch_cells_reorder(const float4* pred_o, const float4* pos_o, float4* pred
 
 int launch_neighbors(const float4* pred_s, const StepConsts& c, const GridBuffers& g,
                      const NeighborList& nl, NRef n, cudaStream_t s) {
-  PBF_LAUNCH(k_neighbors, grid_for(n.n, 128), 128, s, pred_s, g.cell_range, g.desc, nl.idx, nl.count, g.status,
-                                                c.inv_h, c.h2, nl.K, n);
+  PBF_LAUNCH(k_neighbors, grid_for(n.n, 128), 128, s, pred_s, g.cell_range, g.desc, g.cell_key, nl.idx, nl.count,
+             g.status, c.inv_h, c.h2, nl.K, n);
   return 1;
 }
 

@@ -38,6 +38,7 @@ struct GridBuffers {
   uint32_t* cell_count; // cell_cap entries, zero between substeps (counting sort)
   uint32_t* cell_excl;  // cell_cap entries: exclusive prefix inside a scan chunk
   uint32_t* slot_id;    // n entries: particle id per slot before the cells are ordered by id
+  unsigned long long* cell_key;  // cell_cap entries: packed coordinates per hash slot (sparse table), else empty
   uint32_t cell_cap;
 };
 
@@ -55,7 +56,7 @@ int launch_unpack_state(const float4* pos_o, const float4* vel_o, float* const s
 // grid tables are bit-exact in both modes).  slab: bounds are taken after migration instead.
 int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConsts& c,
                    const GridBuffers& g, NRef n, bool slab, cudaStream_t s);
-int launch_grid_finalize(const GridBuffers& g, int pad, cudaStream_t s);
+int launch_grid_finalize(const GridBuffers& g, int pad, NRef n, cudaStream_t s);
 // a4+a5+a6: dense keys, counting sort by cell, cell start/end table.  launch_cells_reorder then
 // orders every cell by particle id (`gid` = global ids in slab mode, nullptr = the slot index),
 // writes the sorted keys / ids to g.keys[*out] / g.vals[*out] and gathers pred/pos into sorted order.

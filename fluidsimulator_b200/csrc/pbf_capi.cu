@@ -140,6 +140,8 @@ int ensure_tables(pbf_ctx* ctx) {
     PBF_CUDA(ctx, ctx->cell_range.reserve(ctx->cell_cap));
     PBF_CUDA(ctx, ctx->cell_count.reserve(ctx->cell_cap));
     PBF_CUDA(ctx, ctx->cell_excl.reserve(ctx->cell_cap));
+    PBF_CUDA(ctx, ctx->cell_key.reserve(ctx->cell_cap));
+    ctx->tables_dirty = true;
     PBF_CUDA(ctx, ctx->chunk_total.reserve(ctx->cell_cap / 2048 + 2));  // one chunk total per 2048 table cells
   }
   if (ctx->slot_id.n < ctx->cap) {
@@ -215,6 +217,7 @@ void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g) {
   g.cell_count = ctx->cell_count.p;
   g.cell_excl = ctx->cell_excl.p;
   g.slot_id = ctx->slot_id.p;
+  g.cell_key = ctx->cell_key.p;
   g.cell_cap = ctx->cell_cap;
 }
 
@@ -326,9 +329,14 @@ int reset_status(pbf_ctx* ctx) {
   for (int a = 0; a < 3; ++a) { z.min_cell[a] = INT_MAX; z.max_cell[a] = INT_MIN; }
   *ctx->status_host = z;
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status.p, ctx->status_host, sizeof(StatusBlock), cudaMemcpyHostToDevice, ctx->stream));
-  // the per-cell counters are zero between substeps; a batch that failed half-way may have left some
-  if (ctx->cell_count.p)
+  // The per-cell counters are zero between substeps and a sparse table is wiped by the next
+  // k_predict; only fresh allocations and a batch that failed half-way need a reset here.
+  if (ctx->tables_dirty && ctx->cell_count.p) {
     PBF_CUDA(ctx, cudaMemsetAsync(ctx->cell_count.p, 0, ctx->cell_count.n * sizeof(uint32_t), ctx->stream));
+    PBF_CUDA(ctx, cudaMemsetAsync(ctx->cell_key.p, 0xff, ctx->cell_key.n * sizeof(unsigned long long), ctx->stream));
+    PBF_CUDA(ctx, cudaMemsetAsync(ctx->desc.p, 0, sizeof(GridDesc), ctx->stream));
+    ctx->tables_dirty = false;
+  }
   return PBF_OK;
 }
 
@@ -430,7 +438,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->vel_a.release(); ctx->vel_b.release(); ctx->omega.release(); ctx->rho.release();
   ctx->planes_dev.release(); ctx->desc.release(); ctx->status.release();
   ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
-  ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release();
+  ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release(); ctx->cell_key.release();
   ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
@@ -564,6 +572,7 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
     }
     // grow and replay the batch from the backup: results never depend on table sizes
     ctx->batches_retried++;
+    ctx->tables_dirty = true;
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     if (st.grid_overflow) {
@@ -664,36 +673,55 @@ int pbf_debug_grid(pbf_ctx* ctx, int32_t* ecx, int32_t* ecy, int32_t* ecz, int32
   if (n == 0) return PBF_OK;
   const GridDesc d = ctx->last_desc;
   std::vector<uint32_t> keys, vals;
-  std::vector<int2> table;
   int rc;
   if ((rc = fetch(ctx, keys, ctx->sorted_buf ? ctx->keys1.p : ctx->keys0.p, n)) != PBF_OK) return rc;
   if ((rc = fetch(ctx, vals, ctx->sorted_buf ? ctx->vals1.p : ctx->vals0.p, n)) != PBF_OK) return rc;
-  if ((rc = fetch(ctx, table, ctx->cell_range.p, (size_t)d.ncells)) != PBF_OK) return rc;
-  const uint32_t dy = (uint32_t)d.dim[1], dz = (uint32_t)d.dim[2];
-  auto decode = [&](uint32_t key, int32_t& x, int32_t& y, int32_t& z) {
-    z = (int32_t)(key % dz) + d.lo[2];
-    y = (int32_t)((key / dz) % dy) + d.lo[1];
-    x = (int32_t)(key / (dz * dy)) + d.lo[0];
-  };
-  for (size_t i = 0; i < n; ++i) {
-    int32_t x, y, z;
-    decode(keys[i], x, y, z);
-    if (ecx) ecx[i] = x;
-    if (ecy) ecy[i] = y;
-    if (ecz) ecz[i] = z;
-    if (eparticle) eparticle[i] = (int32_t)vals[i];
+  // cell coordinates per device slot
+  std::vector<int32_t> x(n), y(n), z(n);
+  if (d.sparse) {
+    std::vector<unsigned long long> cell_key;
+    if ((rc = fetch(ctx, cell_key, ctx->cell_key.p, (size_t)d.ncells)) != PBF_OK) return rc;
+    for (size_t i = 0; i < n; ++i) {
+      const unsigned long long k = cell_key[keys[i]];
+      x[i] = (int32_t)(k >> 42) + d.lo[0];
+      y[i] = (int32_t)((k >> 21) & 0x1fffffu) + d.lo[1];
+      z[i] = (int32_t)(k & 0x1fffffu) + d.lo[2];
+    }
+  } else {
+    const uint32_t dy = (uint32_t)d.dim[1], dz = (uint32_t)d.dim[2];
+    for (size_t i = 0; i < n; ++i) {
+      z[i] = (int32_t)(keys[i] % dz) + d.lo[2];
+      y[i] = (int32_t)((keys[i] / dz) % dy) + d.lo[1];
+      x[i] = (int32_t)(keys[i] / (dz * dy)) + d.lo[0];
+    }
   }
+  // The reference order is lexicographic in (x, y, z), then particle id (core.cpp:12-21, 182).
+  // A dense table stores the slots in that order already; a sparse one stores the cells in hash
+  // order (each cell still contiguous and ordered by id), so the slots are re-ordered here.
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+  if (d.sparse)
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      if (x[a] != x[b]) return x[a] < x[b];
+      if (y[a] != y[b]) return y[a] < y[b];
+      return z[a] < z[b];
+    });
   size_t k = 0;
-  for (uint32_t c = 0; c < d.ncells; ++c) {
-    const int2 r = table[c];
-    if (r.y <= r.x) continue;
-    int32_t x, y, z;
-    decode(c, x, y, z);
-    if (cell_xyz) { cell_xyz[3 * k] = x; cell_xyz[3 * k + 1] = y; cell_xyz[3 * k + 2] = z; }
-    if (cell_start) cell_start[k] = r.x;
-    if (cell_end) cell_end[k] = r.y;
-    ++k;
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t s = order[i];
+    if (ecx) ecx[i] = x[s];
+    if (ecy) ecy[i] = y[s];
+    if (ecz) ecz[i] = z[s];
+    if (eparticle) eparticle[i] = (int32_t)vals[s];
+    const bool first = i == 0 || x[s] != x[order[i - 1]] || y[s] != y[order[i - 1]] || z[s] != z[order[i - 1]];
+    if (first) {  // run-length table (core.cpp:185-203)
+      if (k > 0 && cell_end) cell_end[k - 1] = (int32_t)i;
+      if (cell_xyz) { cell_xyz[3 * k] = x[s]; cell_xyz[3 * k + 1] = y[s]; cell_xyz[3 * k + 2] = z[s]; }
+      if (cell_start) cell_start[k] = (int32_t)i;
+      ++k;
+    }
   }
+  if (k > 0 && cell_end) cell_end[k - 1] = (int32_t)n;
   return PBF_OK;
 }
 
@@ -792,10 +820,15 @@ uint64_t pbf_launch_count(const pbf_ctx* ctx) { return ctx ? ctx->launch_count :
 int pbf_debug_set_capacity(pbf_ctx* ctx, int K, uint32_t cell_cap) {
   if (!ctx || K < 2 || cell_cap < 8) return PBF_E_INVALID;
   ctx->K = (K + 1) & ~1;
-  ctx->cell_cap = cell_cap;
+  uint32_t cap = 8;  // a power of two: the sparse table masks with cell_cap - 1
+  while (cap < cell_cap) cap <<= 1;
+  ctx->cell_cap = cap;
   invalidate_graph(ctx);
   return PBF_OK;
 }
+
+// Test hook (not in pbf_b200.h): 1 if the last substep used the sparse (hashed) cell table.
+int pbf_debug_grid_is_sparse(pbf_ctx* ctx) { return ctx ? ctx->last_desc.sparse : -1; }
 
 // ---------------------------------------------------------------- slab decomposition
 // Implemented in pbf_slab.cu.

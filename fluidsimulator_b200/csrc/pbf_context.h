@@ -139,7 +139,9 @@ struct pbf_ctx {
   pbf::DevBuf<uint32_t> keys0, keys1, vals0, vals1, chunk_total;
   pbf::DevBuf<int2> cell_range;
   pbf::DevBuf<uint32_t> cell_count, cell_excl, slot_id;
-  uint32_t cell_cap = 1u << 22;
+  pbf::DevBuf<unsigned long long> cell_key;  // sparse cell table (hash slots), all-ones when empty
+  uint32_t cell_cap = 1u << 22;   // a power of two (the sparse table masks with cell_cap - 1)
+  bool tables_dirty = true;       // cell counters / sparse keys / descriptor need a reset before the next batch
   int sorted_buf = 0;  // which keys/vals buffer holds the last substep's sorted order
   // neighbour list
   pbf::DevBuf<uint32_t> nbr_idx, nbr_count;

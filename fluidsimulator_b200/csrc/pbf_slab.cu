@@ -485,7 +485,7 @@ int slab_substep(pbf_ctx* ctx) {
     k += launch_slab_merge(ctx->pos_o.p, ctx->pred_o.p, sb, c, hop == sl.hops - 1, s);
     t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
   }
-  launches += launch_grid_finalize(g, 2, s);
+  launches += launch_grid_finalize(g, 2, n_own, s);
   t.launches[PBF_STAGE_PREDICT] += 1;
 
   int out = 0;
@@ -715,6 +715,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     invalidate_graph(ctx);
     // Grow whatever overflowed (identically on every rank) and replay the batch from the backup.
     ctx->batches_retried++;
+    ctx->tables_dirty = true;
     if (st.grid_overflow) {
       const unsigned long long max_cells = ((unsigned long long)st.max_cells_hi << 32) | st.max_cells_lo;
       if (max_cells > (1ull << 30))

@@ -198,3 +198,25 @@ def test_fluid_million_properties(built):
             assert np.array_equal(fwd, bwd)                                   # j in N(i) <=> i in N(j)
     for a, b in zip(*outs):
         assert H.bit_equal(a, b)
+
+
+def test_strict_follows_the_reference_through_its_blow_up(built):
+    """With vorticity on the reference diverges: within ~15 substeps particles fly
+    kilometres away and the bounding box of occupied cells no longer fits a dense table.  The
+    backend switches to the sparse (hashed) cell table and stays bit-identical — state, grid
+    tables in reference order, neighbour lists."""
+    import ctypes as C
+    sol, orc, params = H.make_pair(scenes.SCENES["fluid_large"], H.ALL_FLAGS)
+    sol.lib.pbf_debug_grid_is_sparse.restype = C.c_int
+    sol.lib.pbf_debug_grid_is_sparse.argtypes = [C.c_void_p]
+    seen_sparse = False
+    for chunk in range(8):
+        sol.step(5)
+        orc.step(5)
+        assert H.compare_state_bits(sol, orc) == [], f"substep {5 * chunk + 5}"
+        if sol.lib.pbf_debug_grid_is_sparse(sol.ctx) == 1 and not seen_sparse:
+            seen_sparse = True
+            assert H.compare_integers(sol, orc) == [], f"sparse tables at substep {5 * chunk + 5}"
+    assert seen_sparse, "the scene was expected to outgrow the dense table"
+    assert H.compare_integers(sol, orc) == []
+    assert H.compare_scratch_bits(sol, orc, params) == []
