@@ -96,6 +96,17 @@ def main():
             str(step): {k: digest(np.asarray(v)) for k, v in snap.items()} for step, snap in snaps.items()}
     snaps = run(scenes.SCENES["fluid_large"], H.ALL_FLAGS, [2], iterations=8)
     digests["runs"]["fluid_large:all:iters8"] = {"2": {k: digest(np.asarray(v)) for k, v in snaps[2].items()}}
+    # 4. the parity configurations BASELINE.json names (configs[0..2]) and the reference's vorticity
+    #    blow-up: by substep 20-25 the box of occupied cells spans kilometres
+    for key, scene, flags, steps, iters in (
+            ("fluid_double_dem:all", "fluid_double_dem", H.ALL_FLAGS, [1, 5, 20], None),
+            ("fluid_double_side:all", "fluid_double_side", H.ALL_FLAGS, [1, 4, 12], None),
+            ("fluid_large:all:blowup", "fluid_large", H.ALL_FLAGS, [25], None),
+            ("fluid_large:stable:iters2", "fluid_large", H.STABLE_FLAGS, [6], 2),
+            ("fluid_xlarge:stable", "fluid_xlarge", H.STABLE_FLAGS, [5], None)):
+        snaps = run(scenes.SCENES[scene], flags, steps, iterations=iters)
+        digests["runs"][key] = {
+            str(step): {k: digest(np.asarray(v)) for k, v in snap.items()} for step, snap in snaps.items()}
     (OUT / "digests.json").write_text(json.dumps(digests, indent=1, sort_keys=True))
     print("wrote", sorted(p.name for p in OUT.iterdir()))
 

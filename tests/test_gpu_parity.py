@@ -137,12 +137,18 @@ def test_strict_matches_golden_small(built, flagname):
         assert np.float32(sol.time) == gold[step]["time"]
 
 
-@pytest.mark.parametrize("run", ["fluid_large:stable", "fluid_large:all", "fluid_large:all:iters8"])
+@pytest.mark.parametrize("run", ["fluid_large:stable", "fluid_large:all", "fluid_large:all:iters8",
+                                 "fluid_large:stable:iters2", "fluid_large:all:blowup", "fluid_double_side:all",
+                                 "fluid_double_dem:all", "fluid_xlarge:stable"])
 def test_strict_matches_golden_digests(built, run):
+    """sha256 of every array the reference leaves behind (state, grid tables, neighbour lists,
+    scratch) on the scenes BASELINE.json names, generated from the unmodified reference by
+    tests/golden/make_golden.py — no CPU replay at test time."""
     gold = G.digests()["runs"][run]
     parts = run.split(":")
     flags = FLAGSETS[parts[1]]
-    sol = _solver(scenes.SCENES[parts[0]], flags, 8 if len(parts) > 2 else None)
+    iters = next((int(p[5:]) for p in parts[2:] if p.startswith("iters")), None)
+    sol = _solver(scenes.SCENES[parts[0]], flags, iters)
     done = 0
     for step in sorted(int(s) for s in gold):
         sol.step(step - done)

@@ -216,3 +216,18 @@ def test_virtual_slabs_rebalance(built):
     counts = grp.owned()
     assert max(counts) - min(counts) < 0.2 * sum(counts)
     grp.close()
+
+
+def test_virtual_slabs_fluid_million(built):
+    """BASELINE.json's headline scene at full size: two slabs == one context, bit for bit
+    (one context is tied to the oracle through properties in test_gpu_parity.py)."""
+    params, planes, state = _scene(scenes.SCENES["fluid_million"], H.STABLE_FLAGS)
+    sol = _single(params, planes, state)
+    grp = SlabGroup([0, 0], params, planes)
+    grp.upload(state)
+    assert abs(grp.owned()[0] - grp.owned()[1]) <= 20000      # cuts on cell layers of 10 000 particles
+    grp.step(1)
+    grp.step(3)
+    sol.step(4)
+    _assert_same(grp, sol, "fluid_million, 2 slabs, 4 substeps")
+    grp.close()
