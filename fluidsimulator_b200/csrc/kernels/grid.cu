@@ -1,8 +1,8 @@
 // grid.cu — neighbour-grid kernels of the PBF substep for sm_100a:
 //   a3  predict / integrate            (reference core/src/core.cpp:150-161)
 //   a4  cell coordinates and keys      (core.cpp:28-34, 164-171)
-//   a5  sort by (x, y, z, particle id) (core.cpp:12-21, 173-183)  -> stable LSD radix sort
-//   a6  cell start/end table           (core.cpp:185-203)         -> dense bbox-relative table
+//   a5  sort by (x, y, z, particle id) (core.cpp:12-21, 173-183)  -> counting sort on a dense cell key
+//   a6  cell start/end table           (core.cpp:185-203)         -> the exclusive scan of that sort
 //   a7  neighbour list                 (core.cpp:205-247)         -> warp-interleaved ELL list
 //
 // Integer results (keys, sorted order, cell table, neighbour sets) are bit-exact with
@@ -11,13 +11,14 @@
 //
 // Key design points
 //   * dense key = ((x-x0)*ny + (y-y0))*nz + (z-z0) over the per-substep bounding box of
-//     occupied cells: order-isomorphic to the reference's lexicographic (x,y,z) compare,
-//     so a STABLE sort of particles presented in id order reproduces the reference's
-//     (key, particle) total order exactly, with ~20 key bits => 3 radix passes.
+//     occupied cells: order-isomorphic to the reference's lexicographic (x,y,z) compare and
+//     small (~19 bits), so cell counts + exclusive scan + placement, with the members of a cell
+//     ranked by particle id, reproduce the reference's (key, particle) total order exactly.
 //   * the table is (start,end) per dense cell, padded by one empty layer so the 27-cell
-//     stencil needs no bounds checks.
-//   * nothing here synchronises with the host: bounds, cell counts and overflow flags
-//     live in device memory (GridDesc / StatusBlock).
+//     stencil needs no bounds checks; a box too large for it (the reference's vorticity blow-up)
+//     switches the substep to a sparse table: same arrays, hashed cell coordinates.
+//   * nothing here synchronises with the host: bounds, cell counts, the dense/sparse decision
+//     and overflow flags live in device memory (GridDesc / StatusBlock).
 #include "pbf_kernels.h"
 
 namespace pbf {
@@ -247,8 +248,8 @@ k_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nch
 // place.  The reference order inside a cell is ascending particle id (core.cpp:182); atomics hand
 // out arrival slots in arbitrary order, so the last kernel ranks every particle among the (few)
 // members of its cell by id — O(occupancy) reads per particle — and writes the final slot together
-// with the gathered positions.  6 launches instead of the 14 of the 3-pass stable radix sort + table
-// this replaced (same bits, 105 -> 55 us at 1 M particles).  In slab mode "particle id" is the
+// with the gathered positions.  6 launches; the 3-pass stable radix sort + run-length table this
+// replaced took 14 (same bits, 105 -> 55 us at 1 M particles).  In slab mode "particle id" is the
 // GLOBAL id (gid): the storage order of a slab's particles is then irrelevant, which is what lets
 // migration fill holes instead of re-packing the slab (kernels/slab.cu).
 __global__ void __launch_bounds__(kThreads)

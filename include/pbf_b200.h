@@ -170,8 +170,8 @@ int pbf_debug_scratch(pbf_ctx* ctx, int scratch_id, float* out);
 
 enum pbf_stage_id {
   PBF_STAGE_PREDICT = 0, /* a3+a4: integrate, cell coordinates, bounds          */
-  PBF_STAGE_SORT,        /* a5: radix sort by cell key                           */
-  PBF_STAGE_CELLS,       /* a6: cell start/end table + reorder into sorted order */
+  PBF_STAGE_SORT,        /* a5+a6: counting sort by cell key, cell start/end     */
+  PBF_STAGE_CELLS,       /* order cells by particle id, reorder into sorted order */
   PBF_STAGE_NEIGHBORS,   /* a7: neighbour list                                   */
   PBF_STAGE_LAMBDA,      /* a8                                                   */
   PBF_STAGE_DELTA,       /* a9+a10 (+a11 on the last iteration)                  */
