@@ -92,7 +92,7 @@ int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts
 // The individual passes (the slab driver puts halo exchanges between them).  `cur` selects the
 // pred ping-pong buffer a pass reads; delta writes pred[cur ^ 1].
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
-                  bool strict, cudaStream_t s);
+                  bool strict, cudaStream_t s, Span span = Span{nullptr, 0});
 int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
                  bool is_final, NRef n, bool strict, cudaStream_t s);
 int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,

@@ -175,15 +175,23 @@ __global__ void k_slab_bounds(const uint32_t* __restrict__ keys, const GridDesc*
   const int n = counts->n_own;
   const GridDesc d = *desc;
   const uint32_t layer = (uint32_t)d.dim[1] * (uint32_t)d.dim[2];
-  int b0 = 0, b1 = 0;
+  int b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+  // owned sorted slots with x-cell < x: a prefix of the sorted order
+  auto below = [&](long long x) -> int {
+    const long long xi = x - d.lo[0];
+    return xi <= 0 ? 0 : (xi >= d.dim[0] ? n : lower_bound_key(keys, n, (uint32_t)xi * layer));
+  };
   if (cut_lo != INT_MIN) {
-    const long long xi = (long long)cut_lo + 2 - d.lo[0];
-    b0 = xi <= 0 ? 0 : (xi >= d.dim[0] ? n : lower_bound_key(keys, n, (uint32_t)xi * layer));
+    b0 = below((long long)cut_lo + 2);
+    c0 = below((long long)cut_lo + 1);
   }
   if (cut_hi != INT_MAX) {
-    const long long xi = (long long)cut_hi - 2 - d.lo[0];
-    b1 = xi <= 0 ? n : (xi >= d.dim[0] ? 0 : n - lower_bound_key(keys, n, (uint32_t)xi * layer));
+    b1 = n - below((long long)cut_hi - 2);
+    c1 = n - below((long long)cut_hi - 1);
   }
+  if (c0 + c1 > n) c1 = n - c0;  // a slab whose first and last layer overlap: everything is boundary
+  counts->c1[0] = c0;
+  counts->c1[1] = c1;
   const int worst = b0 > b1 ? b0 : b1;
   atomicMax(&st->max_ghost, (unsigned int)worst);
   if (worst > gcap) {  // never packed (the batch is replayed): tell the receivers so

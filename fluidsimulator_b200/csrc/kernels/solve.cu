@@ -279,14 +279,13 @@ template <bool S>
 __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
-         const StatusBlock* st, DebugPtrs dbg, int K, NRef nr) {
+         const StatusBlock* st, DebugPtrs dbg, Span span, int K, NRef nr) {
   pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
   if (batch_failed(st)) return;
-  const int n = nr.get();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int i = span.slot(blockIdx.x * blockDim.x + threadIdx.x, nr.get());
+  if (i < 0) return;
   const float4 pi = pred[i];
   float rho = 0.0f, gsx = 0.0f, gsy = 0.0f, gsz = 0.0f, sum_grad2 = 0.0f;
   using A = A1<S>;
@@ -615,11 +614,14 @@ k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
 static inline int blocks_for(NRef n) { return (n.n + kBlock - 1) / kBlock; }
 
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
-                  bool strict, cudaStream_t s) {
+                  bool strict, cudaStream_t s, Span span) {
+  // n.n bounds the thread count; with a span it is the caller's bound for that part
   if (strict)
-    PBF_LAUNCH(k_lambda<true>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+    PBF_LAUNCH(k_lambda<true>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, span,
+               nl.K, n);
   else
-    PBF_LAUNCH(k_lambda<false>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, nl.K, n);
+    PBF_LAUNCH(k_lambda<false>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, span,
+               nl.K, n);
   return 1;
 }
 

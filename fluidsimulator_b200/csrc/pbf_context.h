@@ -96,6 +96,9 @@ struct SlabState {
   DevBuf<uint32_t> holes;                  // 6 * mcap: slots vacated by migrants + two scratch lists
   DevBuf<float4> send[2][2], recv[2];      // [parity][side], [side]
   SlabCounts* counts_host = nullptr;       // pinned
+  cudaStream_t side = nullptr;             // halo of iteration k in flight while lambda runs on the interior
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = false;                    // PBF_SLAB_OVERLAP=1: split lambda pass (measured slower at 8 x 2 M, see pbf_slab.cu)
   std::vector<uint32_t> gid_host;          // staging of global ids for upload / download
 };
 

@@ -382,6 +382,10 @@ int ensure_slab_buffers(pbf_ctx* ctx) {
     PBF_CUDA(ctx, cudaMemset(sl.counts.p, 0, sizeof(SlabCounts)));
     PBF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&sl.counts_host), sizeof(SlabCounts)));
     std::memset(sl.counts_host, 0, sizeof(SlabCounts));
+    PBF_CUDA(ctx, cudaStreamCreateWithFlags(&sl.side, cudaStreamNonBlocking));
+    PBF_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+    PBF_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming));
+    if (const char* e = std::getenv("PBF_SLAB_OVERLAP")) sl.overlap = e[0] != '0';
   }
   PBF_CUDA(ctx, sl.holes.reserve(6 * (size_t)sl.mcap + 64));
   const size_t elems = 1 + 2 * (size_t)std::max(sl.mcap, sl.gcap);
@@ -517,12 +521,22 @@ int slab_substep(pbf_ctx* ctx) {
     t.launches[PBF_STAGE_FINALIZE] += 1;
     return launches;
   }
+  // Only the first cell layer next to a cut reads ghosts.  Optionally (PBF_SLAB_OVERLAP=1) the
+  // lambda pass after iteration 0 is split: its interior part starts right after the delta pass
+  // while the halo of that pass is exchanged, unpacked and followed by the boundary part on a side
+  // stream.  MEASURED on B200: no gain at 2 slabs (1.671 vs 1.666 ms at 2 M particles per GPU) and
+  // a loss at 8 (2.49 vs 2.00 ms: the boundary pass with ~0.5 M ghosts competes with the interior
+  // pass for the same SMs and the fork/join adds two graph edges per iteration), so it is off.
+  const bool overlap = sl.overlap && sl.nranks > 1 && !ctx->profile;
+  const NRef n_interior = nref((int)ctx->cap, &sl.counts.p->n_own);
+  const NRef n_boundary = nref(4 * sl.gcap, &sl.counts.p->n_tot);
   int cur = 0;
+  stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
+  launches += launch_lambda(b, nl, c, cur, n_tot, strict, s);  // owned + first-layer ghosts
+  stage_mark(ctx, PBF_STAGE_LAMBDA, 0);
+  t.launches[PBF_STAGE_LAMBDA] += 1;
   for (int it = 0; it < iters; ++it) {
     const bool last = it == iters - 1;
-    stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
-    launches += launch_lambda(b, nl, c, cur, n_tot, strict, s);  // owned + first-layer ghosts
-    stage_mark(ctx, PBF_STAGE_LAMBDA, 0);
     // the delta pass stores its two boundary layers straight into the outgoing messages (no pack
     // kernel); after the very last pass nothing reads the ghosts any more
     const bool refresh = !(last && final_in_delta);
@@ -535,14 +549,36 @@ int slab_substep(pbf_ctx* ctx) {
     launches += launch_delta(b, nl, c, cur, last, last && final_in_delta, n_own, strict, s);
     stage_mark(ctx, PBF_STAGE_DELTA, 0);
     b.halo = HaloOut{nullptr, {nullptr, nullptr}};
-    t.launches[PBF_STAGE_LAMBDA] += 1;
     t.launches[PBF_STAGE_DELTA] += 1;
     cur ^= 1;
     if (!refresh) break;
-    k = 0;
-    if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
-    k += launch_slab_halo_unpack(b.pred[cur], sb, s);
-    t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
+    if (last || !overlap) {
+      if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
+      k = launch_slab_halo_unpack(b.pred[cur], sb, s);
+      t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
+      if (!last) {
+        stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
+        launches += launch_lambda(b, nl, c, cur, n_tot, strict, s);
+        stage_mark(ctx, PBF_STAGE_LAMBDA, 0);
+        t.launches[PBF_STAGE_LAMBDA] += 1;
+      }
+      continue;
+    }
+    // fork: [side] exchange -> unpack -> lambda(boundary + ghosts)   ||   [main] lambda(interior)
+    if (cudaEventRecord(sl.ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(sl.side, sl.ev_fork, 0) != cudaSuccess)
+      return fail(ctx, PBF_E_CUDA, "slab substep: fork onto the halo stream failed");
+    ctx->stream = sl.side;  // the transport enqueues on the context's stream
+    rc = slab_exchange(ctx, sb, (size_t)sl.gcap);
+    ctx->stream = s;
+    if (rc != PBF_OK) return rc;
+    k = launch_slab_halo_unpack(b.pred[cur], sb, sl.side);
+    k += launch_lambda(b, nl, c, cur, n_boundary, strict, sl.side, Span{sl.counts.p, 1});
+    k += launch_lambda(b, nl, c, cur, n_interior, strict, s, Span{sl.counts.p, 0});
+    if (cudaEventRecord(sl.ev_join, sl.side) != cudaSuccess || cudaStreamWaitEvent(s, sl.ev_join, 0) != cudaSuccess)
+      return fail(ctx, PBF_E_CUDA, "slab substep: join of the halo stream failed");
+    t.launches[PBF_STAGE_LAMBDA] += 2;
+    t.launches[PBF_STAGE_EXCHANGE] += 1;
+    launches += k;
   }
   if (final_in_delta) return launches;
 
@@ -604,6 +640,11 @@ void slab_release(pbf_ctx* ctx) {
   sl.recv[0].release(); sl.recv[1].release();
   if (sl.counts_host) cudaFreeHost(sl.counts_host);
   sl.counts_host = nullptr;
+  if (sl.side) cudaStreamDestroy(sl.side);
+  if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
+  if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+  sl.side = nullptr;
+  sl.ev_fork = sl.ev_join = nullptr;
 }
 
 // pbf_step of a slab context.  Every rank of the communicator (or every thread of the group)
