@@ -25,6 +25,9 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+# BASELINE.json: "particle-substeps/sec @1M particles, 4 iters (1/2/4/8 B200) + % HBM roofline"
+METRIC = "particle-substeps/sec (PBF substep, 4 solver iterations)"
+
 FLAGSETS = {
     "none": dict(scorr=0, xsph=0, vort=0, rest=0.0, fric=0.0),
     "stable": dict(scorr=1, xsph=1, vort=0, rest=0.05, fric=0.1),
@@ -171,7 +174,7 @@ def run_reference(args, flags):
     total = float(sum(per))
     value = n * args.steps / total
     line = {
-        "impl": "reference", "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-substeps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -292,7 +295,7 @@ def run_ours(args, flags):
                         "kind": kind, "sample": f"{args.scene} from t0, 1 warm-up + {len(per)} timed substeps, all host threads"}
 
     line = {
-        "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": 1,
+        "metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.scene, "particles": n, "solver_iterations": args.iterations, "flags": args.flags,

@@ -199,7 +199,7 @@ def bench(args, flags, rank: int, world: int, local: int):
                     "alg_bytes_per_particle": B.ALG_BYTES[dom], "avg_launch_ms": per_launch_s * 1e3,
                     "whole_step_frac": B.b_alg(args.iterations, flags) * value / 1e9 / (peak * world)}
     line = {
-        "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+        "metric": B.METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": scene, "particles": n, "solver_iterations": args.iterations, "flags": args.flags,

@@ -19,7 +19,7 @@ def test_reference_arm_prints_the_contract_line(built):
                           "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["impl"] == "reference" and line["metric"] == "particle-substeps/s" and line["value"] > 0
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == "particle-substeps/s" and line["value"] > 0
     assert line["config"]["workload"] == "fluid_large" and line["config"]["particles"] == 19683
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
