@@ -134,6 +134,11 @@ def test_frame_bytes_match_reference_writer(built, tmp_path):
     (["--no-output=1"], "Option does not take a value: --no-output"),
     (["--backend", "cpu"], "Unsupported backend: cpu"),
     (["--backend", "metal"], "Unsupported backend: metal"),
+    (["--devices", "0,x"], "Invalid devices value"),
+    (["--devices", "0,-1"], "Invalid devices value"),
+    (["--devices", "0,1", "--per-step-host"], "--devices and --per-step-host exclude each other."),
+    (["--mode", "sloppy"], "mode must be strict or fast."),
+    (["--solver-iterations", "-2"], "solver-iterations must be >= 0."),
 ])
 def test_app_argument_validation(built, args, msg):
     """Same validation and messages as reference app/src/main.cpp:78-166 / cli.cpp:34-101."""
@@ -147,5 +152,5 @@ def test_app_help(built):
     assert r.returncode == 0
     for opt in ["backend", "no-output", "debug-print", "steps", "steps-per-sec", "enable-scorr", "enable-xsph",
                 "enable-vorticity", "plane-restitution", "plane-friction", "threads", "no-omp", "fps", "duration",
-                "scene", "output-dir", "solver-iterations"]:
+                "scene", "output-dir", "solver-iterations", "mode", "device", "devices", "per-step-host"]:
         assert f"--{opt}" in r.stdout
