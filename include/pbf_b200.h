@@ -144,7 +144,9 @@ int pbf_set_time(pbf_ctx* ctx, float t);
 int pbf_debug_sizes(pbf_ctx* ctx, size_t* ncells, size_t* nneighbors);
 /* grid_entries (core.h:112): per sorted slot the cell coordinates and particle id;
  * grid_keys/grid_starts/grid_ends (core.h:113-115): per occupied cell.
- * Arrays: entry_* [n]; cell_xyz [3*ncells] (x,y,z interleaved); cell_start/end [ncells]. */
+ * Arrays: entry_* [n]; cell_xyz [3*ncells] (x,y,z interleaved); cell_start/end [ncells].
+ * Always in the reference's order (lexicographic x, y, z, then particle id), also when the
+ * substep used the sparse cell table.  On a slab context: the slab's own particles, local ids. */
 int pbf_debug_grid(pbf_ctx* ctx, int32_t* entry_cx, int32_t* entry_cy,
                    int32_t* entry_cz, int32_t* entry_particle, int32_t* cell_xyz,
                    int32_t* cell_start, int32_t* cell_end);
@@ -202,7 +204,9 @@ uint64_t pbf_launch_count(const pbf_ctx* ctx);
  * x-cells [cuts[r], cuts[r+1]).  Cell of a position: floor(x * (1.0f / h)) (core.cpp:28-34). */
 int pbf_slab_plan(size_t n, const float* px, float h, int nranks, int32_t* cuts);
 
-/* Multi-process transport (NCCL send/recv between x-neighbours). */
+/* Multi-process transport: one NCCL communicator over the slabs.  It carries the halo messages
+ * themselves (ncclSend/ncclRecv between x-neighbours) or, by default, only the cudaIpc handles of
+ * the peer windows and the per-batch status reduction (see pbf_slab_set_p2p). */
 #define PBF_COMM_ID_BYTES 128
 /* Rank 0 calls this and ships the bytes to every rank by any host channel
  * (torch.distributed broadcast, a file, MPI...). */
