@@ -86,3 +86,36 @@ def max_abs_pos_err_in_h(sol: Solver, orc: Oracle, h: float) -> float:
 def max_abs_vel_err(sol: Solver, orc: Oracle) -> float:
     a, b = sol.download(), orc.get_state()
     return float(max(np.max(np.abs(a[k].astype(np.float64) - b[k].astype(np.float64))) for k in range(3, 6)))
+
+
+def random_cloud(seed: int, n: int | None = None):
+    """(params, planes, state, flags) of an adversarial random particle cloud: particles snapped onto
+    cell boundaries, coincident particles, negative coordinates, particles outside the planes, fast
+    and resting ones, ragged counts (n not a multiple of 32).  Deterministic in `seed`."""
+    rng = np.random.default_rng(seed)
+    if n is None:
+        n = int(rng.choice([1, 2, 31, 32, 33, 97, 257, 600]))
+    h = np.float32(0.1)
+    pos = rng.uniform(-0.35, 0.65, size=(3, n)).astype(np.float32)
+    snap = rng.random(n) < 0.25                       # exactly on a cell boundary along some axis
+    axis = rng.integers(0, 3, size=n)
+    cells = np.round(pos[axis, np.arange(n)] / h).astype(np.float32)
+    pos[axis[snap], np.nonzero(snap)[0]] = (cells[snap] * h).astype(np.float32)
+    if n > 3:                                          # coincident particles (r = 0 pairs)
+        dup = rng.integers(0, n, size=max(1, n // 20))
+        src = rng.integers(0, n, size=dup.shape[0])
+        pos[:, dup] = pos[:, src]
+    vel = (rng.normal(0.0, 1.5, size=(3, n)) * (rng.random(n) < 0.8)).astype(np.float32)
+    params = PbfParams.defaults()
+    params.particle_mass, params.density, params.h, params.epsilon = 1.0, 6000.0, float(h), 300.0
+    params.scorr_k, params.scorr_n, params.visc_c = 0.0005, int(rng.choice([2, 3, 4])), 0.0005
+    flags = dict(scorr=int(rng.integers(0, 2)), xsph=int(rng.integers(0, 2)), vort=int(rng.integers(0, 2)),
+                 rest=float(rng.choice([0.0, 0.05])), fric=float(rng.choice([0.0, 0.1])))
+    params = configure(params, flags, iterations=int(rng.choice([1, 2, 4])))
+    lo, hi = -0.3, 0.6                                 # some particles start outside the box
+    planes = np.array([[0, 1, 0, lo], [1, 0, 0, lo], [0, 0, 1, lo],
+                       [0, -1, 0, -hi], [-1, 0, 0, -hi], [0, 0, -1, -hi]], dtype=np.float32)
+    if rng.random() < 0.3:
+        planes = planes[: int(rng.integers(0, 4))]     # fewer planes, possibly none
+    state = [np.ascontiguousarray(pos[k]) for k in range(3)] + [np.ascontiguousarray(vel[k]) for k in range(3)]
+    return params, planes, state, flags
