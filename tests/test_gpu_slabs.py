@@ -182,8 +182,12 @@ def test_virtual_slabs_iterations_and_fast_mode(built):
     grp.close()
 
 
-def test_nccl_slabs_two_gpus(built):
-    """Two processes, one GPU each, NCCL halo exchange (skipped on a 1-GPU box)."""
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["peer-stores", "nccl-messages"])
+def test_nccl_slabs_two_gpus(built, p2p):
+    """Two processes, one GPU each (skipped on a 1-GPU box): halos by direct stores into the
+    neighbour's cudaIpc window (default) and by ncclSend/ncclRecv messages (PBF_SLAB_P2P=0); the
+    second half of the run replays the captured CUDA graph with the exchanges inside."""
+    import os
     import subprocess
     import sys
     from fluidsimulator_b200 import capi
@@ -191,9 +195,10 @@ def test_nccl_slabs_two_gpus(built):
         pytest.skip("needs 2 GPUs")
     root = H.scenes.__file__.rsplit("/fluidsimulator_b200/", 1)[0]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", "-m", "fluidsimulator_b200.multigpu",
-           "--check", "--scene", "fluid_large", "--steps", "10"]
-    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+           "--master-addr", "127.0.0.1", "--master-port", "29517" if p2p == "1" else "29518",
+           "-m", "fluidsimulator_b200.multigpu", "--check", "--scene", "fluid_large", "--steps", "10"]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PBF_SLAB_P2P=p2p))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "slab check ok" in out.stdout
 
