@@ -164,6 +164,8 @@ ABI = {
     "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
     "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
     "pbf_slab_set_cuts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "pbf_slab_set_rebalance": (C.c_int, [C.c_void_p, C.c_float]),
+    "pbf_slab_rebalance_count": (C.c_uint64, [C.c_void_p]),
     "pbf_slab_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32p, _i32p]),
     "pbf_group_create": (C.c_void_p, [C.POINTER(C.c_void_p), C.c_int]),
     "pbf_group_destroy": (None, [C.c_void_p]),
@@ -391,6 +393,12 @@ class SlabSolver(Solver):
 
     def set_cuts(self, lo: int, hi: int):
         self._check(self.lib.pbf_slab_set_cuts(self.ctx, int(lo), int(hi)))
+
+    def set_rebalance(self, threshold: float):
+        self._check(self.lib.pbf_slab_set_rebalance(self.ctx, C.c_float(threshold)))
+
+    def rebalance_count(self) -> int:
+        return int(self.lib.pbf_slab_rebalance_count(self.ctx))
 
     def slab_download(self, out=None):
         """(global ids, six SoA arrays) of the owned particles.  `out` = (int64 array, six float32

@@ -315,6 +315,36 @@ k_slab_ghost_vel(const float4* __restrict__ pred, const float4* __restrict__ pos
   vel[i] = make_float4(vx, vy, vz, inv_rho);
 }
 
+// ---------------------------------------------------------------- re-balancing support
+__global__ void k_slab_report(const SlabCounts* __restrict__ counts, StatusBlock* st, int rank) {
+  pdl_wait();
+  if (rank < kMaxSlabs) st->own_by_rank[rank] = (unsigned int)counts->n_own;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_slab_xrange(const float4* __restrict__ pos_o, const SlabCounts* __restrict__ counts, float inv_h, int* out) {
+  pdl_wait();
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  int lo = INT_MAX, hi = INT_MIN;
+  if (i < counts->n_own) lo = hi = cell_coord(pos_o[i].x, inv_h);
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0 && lo != INT_MAX) {
+    atomicMin(&out[0], lo);
+    atomicMax(&out[1], hi);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_slab_xhist(const float4* __restrict__ pos_o, const SlabCounts* __restrict__ counts, float inv_h, int x_min,
+             int layers, unsigned long long* __restrict__ hist) {
+  pdl_wait();
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= counts->n_own) return;
+  const long long l = (long long)cell_coord(pos_o[i].x, inv_h) - x_min;
+  if (l >= 0 && l < layers) atomicAdd(&hist[l], 1ull);
+}
+
 inline int grid_for(int n) { return (n + kThreads - 1) / kThreads; }
 
 }  // namespace
@@ -356,6 +386,22 @@ int launch_slab_ghost_unpack(float4* pred_s, float4* pos_s, const GridBuffers& g
 int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s) {
   PBF_LAUNCH(k_slab_halo_unpack, grid_for(2 * sb.gcap), kThreads, s, sb.recv[0], sb.recv[1], arr, sb.counts, sb.status,
                                                                sb.gcap);
+  return 1;
+}
+
+int launch_slab_report(const SlabBuffers& sb, int rank, cudaStream_t s) {
+  PBF_LAUNCH(k_slab_report, 1, 1, s, sb.counts, sb.status, rank);
+  return 1;
+}
+
+int launch_slab_xrange(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int* out_min_max, cudaStream_t s) {
+  PBF_LAUNCH(k_slab_xrange, grid_for(sb.cap), kThreads, s, pos_o, sb.counts, c.inv_h, out_min_max);
+  return 1;
+}
+
+int launch_slab_xhist(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int x_min, int layers,
+                      unsigned long long* hist, cudaStream_t s) {
+  PBF_LAUNCH(k_slab_xhist, grid_for(sb.cap), kThreads, s, pos_o, sb.counts, c.inv_h, x_min, layers, hist);
   return 1;
 }
 

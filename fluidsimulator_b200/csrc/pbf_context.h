@@ -57,6 +57,8 @@ struct Transport {
   virtual int reduce_status_device(pbf_ctx* ctx, unsigned int* dev_words, int count) = 0;
   // ... or of its host copy after the batch's synchronisation (whichever the transport supports)
   virtual int reduce_status_host(pbf_ctx* ctx, unsigned int* host_words, int count) = 0;
+  // all-reduce of a small host array over all slabs (op 0 = max, 1 = sum); blocking, collective
+  virtual int allreduce_host(pbf_ctx* ctx, long long* words, int count, int op) = 0;
   virtual void abort() {}
   // true when exchange() is purely stream-ordered, i.e. may be recorded into a CUDA graph
   virtual bool capturable() const { return false; }
@@ -88,6 +90,9 @@ struct SlabState {
   uint64_t graph_exchanges = 0, graph_bytes = 0;  // per replay of the captured substep
   bool warm = false;                       // a batch has completed since the communicator was joined
   bool fixed_caps = false;                 // keep the message capacities (no adaptive shrinking)
+  float rebalance_threshold = 1.3f;        // re-plan the cuts when max / mean owned exceeds it (0 = never)
+  uint64_t rebalances = 0;
+  DevBuf<unsigned long long> hist_dev;     // x-layer histogram / staging of host all-reduces
   int want_p2p = -1;                       // direct peer stores instead of messages: -1 = default for the transport
   Transport* transport = nullptr;          // not owned when it belongs to a group
   bool owns_transport = false;

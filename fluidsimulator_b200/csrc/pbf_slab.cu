@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -31,12 +32,37 @@ inline int host_cell(float x, float inv_h) {
 }
 
 // Cuts on x-cell boundaries with (nearly) equal particle counts; every slab at least two cells
-// wide so that both ghost layers of a slab come from its direct neighbour.
-int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& cuts, std::string& err) {
+// wide so that both ghost layers of a slab come from its direct neighbour.  hist[l] = particles in
+// the x-layer lo + l.
+int plan_cuts_hist(const std::vector<size_t>& hist, int lo, int nranks, std::vector<int>& cuts, std::string& err) {
   cuts.assign((size_t)nranks + 1, 0);
   cuts[0] = INT_MIN;
   cuts[nranks] = INT_MAX;
   if (nranks == 1) return PBF_OK;
+  const long long layers = (long long)hist.size();
+  size_t n = 0;
+  for (size_t c : hist) n += c;
+  if (n == 0 || layers < 2LL * nranks) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "slab plan: %lld x-layers of cells can not be split into %d slabs of >= 2 layers",
+                  layers, nranks);
+    err = buf;
+    return PBF_E_INVALID;
+  }
+  size_t cum = 0;
+  long long layer = 0;
+  for (int r = 1; r < nranks; ++r) {
+    const size_t target = (size_t)(((unsigned long long)n * (unsigned)r) / (unsigned)nranks);
+    const long long min_layer = (r == 1 ? 0 : (long long)cuts[r - 1] - lo) + 2;  // this slab >= 2 layers
+    const long long max_layer = layers - 2LL * (nranks - r);                      // room for the rest
+    while (layer < max_layer && (layer < min_layer || cum + hist[(size_t)layer] / 2 < target)) cum += hist[(size_t)layer++];
+    cuts[r] = (int)(lo + layer);
+  }
+  return PBF_OK;
+}
+
+int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& cuts, std::string& err) {
+  if (nranks == 1) return plan_cuts_hist({}, 0, 1, cuts, err);
   if (n == 0) {
     err = "slab plan: no particles";
     return PBF_E_INVALID;
@@ -49,25 +75,13 @@ int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& 
     hi = std::max(hi, c);
   }
   const long long layers = (long long)hi - lo + 1;
-  if (lo == INT_MIN || layers < 2LL * nranks || layers > (1LL << 24)) {
-    char buf[160];
-    std::snprintf(buf, sizeof(buf), "slab plan: %lld x-layers of cells can not be split into %d slabs of >= 2 layers",
-                  layers, nranks);
-    err = buf;
+  if (lo == INT_MIN || layers > (1LL << 24)) {
+    err = "slab plan: non-finite or absurdly spread x coordinates";
     return PBF_E_INVALID;
   }
   std::vector<size_t> hist((size_t)layers, 0);
   for (size_t i = 0; i < n; ++i) hist[(size_t)(host_cell(px[i], inv_h) - lo)]++;
-  size_t cum = 0;
-  long long layer = 0;
-  for (int r = 1; r < nranks; ++r) {
-    const size_t target = (size_t)(((unsigned long long)n * (unsigned)r) / (unsigned)nranks);
-    const long long min_layer = (r == 1 ? 0 : (long long)cuts[r - 1] - lo) + 2;  // this slab >= 2 layers
-    const long long max_layer = layers - 2LL * (nranks - r);                      // room for the rest
-    while (layer < max_layer && (layer < min_layer || cum + hist[(size_t)layer] / 2 < target)) cum += hist[(size_t)layer++];
-    cuts[r] = (int)(lo + layer);
-  }
-  return PBF_OK;
+  return plan_cuts_hist(hist, lo, nranks, cuts, err);
 }
 
 }  // namespace
@@ -115,6 +129,16 @@ struct NcclTransport : Transport {
     return PBF_OK;
   }
   int reduce_status_host(pbf_ctx*, unsigned int*, int) override { return PBF_OK; }
+  int allreduce_host(pbf_ctx* ctx, long long* words, int count, int op) override {
+    if (nranks == 1) return PBF_OK;
+    PBF_CUDA(ctx, ctx->slab.hist_dev.reserve((size_t)count));
+    void* d = ctx->slab.hist_dev.p;
+    PBF_CUDA(ctx, cudaMemcpyAsync(d, words, (size_t)count * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    PBF_NCCL(ctx, ncclAllReduce(d, d, (size_t)count, ncclInt64, op == 0 ? ncclMax : ncclSum, comm, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(words, d, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PBF_OK;
+  }
   bool capturable() const override { return true; }  // ncclSend/ncclRecv record into a CUDA graph
 };
 
@@ -133,6 +157,7 @@ struct pbf_group {
   std::vector<cudaEvent_t> packed;                 // per rank
   std::vector<float4*> send_ptr[2];                // [side][rank], published per exchange
   std::vector<std::vector<unsigned int>> words;    // status agreement
+  std::vector<std::vector<long long>> wide;        // host all-reduces
   std::vector<float4*> window;                     // peer windows (direct-store transport)
   // global ids for upload / download
   size_t n_global = 0;
@@ -190,6 +215,20 @@ struct LocalTransport : Transport {
     if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
     for (int p = 0; p < nr; ++p)
       for (int k = 0; k < count; ++k) host_words[k] = std::max(host_words[k], g->words[p][k]);
+    if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    return PBF_OK;
+  }
+  int allreduce_host(pbf_ctx* ctx, long long* words, int count, int op) override {
+    pbf_group* g = group;
+    const int r = ctx->slab.rank, nr = ctx->slab.nranks;
+    if (nr == 1) return PBF_OK;
+    g->wide[r].assign(words, words + count);
+    if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
+    for (int k = 0; k < count; ++k) {
+      long long v = g->wide[0][k];
+      for (int p = 1; p < nr; ++p) v = op == 0 ? std::max(v, g->wide[p][k]) : v + g->wide[p][k];
+      words[k] = v;
+    }
     if (!g->barrier()) return fail(ctx, PBF_E_COMM, "slab group aborted by another rank");
     return PBF_OK;
   }
@@ -368,6 +407,7 @@ struct PeerTransport : Transport {
   }
   int reduce_status_device(pbf_ctx* ctx, unsigned int* w, int n) override { return inner->reduce_status_device(ctx, w, n); }
   int reduce_status_host(pbf_ctx* ctx, unsigned int* w, int n) override { return inner->reduce_status_host(ctx, w, n); }
+  int allreduce_host(pbf_ctx* ctx, long long* w, int n, int op) override { return inner->allreduce_host(ctx, w, n, op); }
   void abort() override { inner->abort(); }
   // Between processes the substep (flag kernels included) replays as a CUDA graph.  Inside one
   // process graph instantiation by one slab could stall behind another slab's spinning kernel.
@@ -628,13 +668,70 @@ int set_device_count(pbf_ctx* ctx, int n_own) {
 
 }  // namespace
 
+namespace {
+
+// Automatic re-balancing.  Every rank sees every slab's owned count in the max-reduced status
+// block; when the largest slab exceeds the mean by the threshold, all ranks together build the
+// x-layer histogram of the whole scene (one sum all-reduce), plan equal-count cuts on it with the
+// planner the upload uses, and install them.  Misplaced particles migrate during the next substep
+// (hop count and message capacities grow on demand), so results do not depend on when this happens.
+int maybe_rebalance(pbf_ctx* ctx, const StatusBlock& st) {
+  SlabState& sl = ctx->slab;
+  if (!(sl.rebalance_threshold > 0.0f) || sl.nranks < 2 || sl.nranks > kMaxSlabs) return PBF_OK;
+  unsigned long long total = 0, largest = 0;
+  for (int r = 0; r < sl.nranks; ++r) {
+    total += st.own_by_rank[r];
+    largest = std::max<unsigned long long>(largest, st.own_by_rank[r]);
+  }
+  if (total == 0 || (double)largest * sl.nranks <= (double)sl.rebalance_threshold * (double)total) return PBF_OK;
+  SlabBuffers sb{};
+  slab_fill(ctx, sb);
+  // global x-cell range of the owned particles
+  PBF_CUDA(ctx, sl.hist_dev.reserve(2));
+  int* range_dev = reinterpret_cast<int*>(sl.hist_dev.p);
+  const int init[2] = {INT_MAX, INT_MIN};
+  PBF_CUDA(ctx, cudaMemcpyAsync(range_dev, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launch_count += (uint64_t)launch_slab_xrange(ctx->pos_o.p, sb, ctx->consts, range_dev, ctx->stream);
+  int range[2];
+  PBF_CUDA(ctx, cudaMemcpyAsync(range, range_dev, sizeof(range), cudaMemcpyDeviceToHost, ctx->stream));
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  long long mm[2] = {ctx->n ? -(long long)range[0] : LLONG_MIN, ctx->n ? (long long)range[1] : LLONG_MIN};
+  int rc = sl.transport->allreduce_host(ctx, mm, 2, 0);
+  if (rc != PBF_OK) return rc;
+  const long long x_min = -mm[0], x_max = mm[1];
+  const long long layers = x_max - x_min + 1;
+  if (layers < 2LL * sl.nranks || layers > (1LL << 16) || x_min < INT_MIN / 2 || x_max > INT_MAX / 2) return PBF_OK;
+  // histogram of the whole scene
+  PBF_CUDA(ctx, sl.hist_dev.reserve((size_t)layers));
+  PBF_CUDA(ctx, cudaMemsetAsync(sl.hist_dev.p, 0, (size_t)layers * sizeof(unsigned long long), ctx->stream));
+  ctx->launch_count += (uint64_t)launch_slab_xhist(ctx->pos_o.p, sb, ctx->consts, (int)x_min, (int)layers, sl.hist_dev.p,
+                                                   ctx->stream);
+  std::vector<long long> hist((size_t)layers);
+  PBF_CUDA(ctx, cudaMemcpyAsync(hist.data(), sl.hist_dev.p, (size_t)layers * sizeof(long long), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = sl.transport->allreduce_host(ctx, hist.data(), (int)layers, 1)) != PBF_OK) return rc;
+  std::vector<size_t> h((size_t)layers);
+  for (size_t l = 0; l < h.size(); ++l) h[l] = (size_t)hist[l];
+  std::vector<int> cuts;
+  std::string err;
+  if (plan_cuts_hist(h, (int)x_min, sl.nranks, cuts, err) != PBF_OK) return PBF_OK;  // can not do better: keep the cuts
+  sl.cut_lo = cuts[(size_t)sl.rank];
+  sl.cut_hi = cuts[(size_t)sl.rank + 1];
+  sl.rebalances++;
+  invalidate_graph(ctx);
+  return PBF_OK;
+}
+
+}  // namespace
+
 namespace pbf {
 
 void slab_release(pbf_ctx* ctx) {
   SlabState& sl = ctx->slab;
   if (sl.owns_transport && sl.transport) delete sl.transport;
   sl.transport = nullptr;
-  sl.counts.release(); sl.gid_o.release(); sl.gid_bak.release(); sl.holes.release();
+  sl.counts.release(); sl.gid_o.release(); sl.gid_bak.release(); sl.holes.release(); sl.hist_dev.release();
   for (int p = 0; p < 2; ++p)
     for (int side = 0; side < 2; ++side) sl.send[p][side].release();
   sl.recv[0].release(); sl.recv[1].release();
@@ -708,6 +805,11 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
         ctx->launch_count += (uint64_t)k;
       }
     }
+    {
+      SlabBuffers sb{};
+      slab_fill(ctx, sb);
+      ctx->launch_count += (uint64_t)launch_slab_report(sb, sl.rank, ctx->stream);
+    }
     PBF_CUDA(ctx, cudaGetLastError());
     unsigned int* dev_words = &ctx->status.p->max_neighbors;
     if ((rc = sl.transport->reduce_status_device(ctx, dev_words, kStatusShared)) != PBF_OK) return rc;
@@ -738,6 +840,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       ctx->n = (size_t)sl.counts_host->n_own;
       for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
       sl.warm = true;
+      if ((rc = maybe_rebalance(ctx, st)) != PBF_OK) return rc;
       // Messages are sent at full capacity (their size is not known to the host), so capacities
       // follow the observed maxima down as well as up.  The maxima are max-reduced over the slabs:
       // every rank takes the same decision.
@@ -985,6 +1088,14 @@ int pbf_slab_set_cuts(pbf_ctx* ctx, int32_t lo, int32_t hi) {
   return PBF_OK;
 }
 
+int pbf_slab_set_rebalance(pbf_ctx* ctx, float threshold) {
+  if (!ctx || !ctx->slab.enabled || !(threshold >= 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_slab_set_rebalance: bad arguments");
+  ctx->slab.rebalance_threshold = threshold;
+  return PBF_OK;
+}
+
+uint64_t pbf_slab_rebalance_count(const pbf_ctx* ctx) { return ctx ? ctx->slab.rebalances : 0; }
+
 int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi) {
   if (!ctx || !ctx->slab.enabled) return PBF_E_INVALID;
   if (lo) *lo = ctx->slab.cut_lo;
@@ -1036,6 +1147,7 @@ pbf_group* pbf_group_create(pbf_ctx** ctxs, int n) {
   g->send_ptr[0].assign((size_t)n, nullptr);
   g->send_ptr[1].assign((size_t)n, nullptr);
   g->words.resize((size_t)n);
+  g->wide.resize((size_t)n);
   g->window.assign((size_t)n, nullptr);
   for (int r = 0; r < n; ++r) {
     cudaSetDevice(ctxs[r]->device);

@@ -241,6 +241,11 @@ int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi);
  * another slab migrate during the next substep (one hop per slab of distance; the hop count
  * grows on demand), so results do not depend on when or how the cuts move. */
 int pbf_slab_set_cuts(pbf_ctx* ctx, int32_t lo, int32_t hi);
+/* Automatic re-balancing: at the end of a pbf_step batch, when the largest slab owns more than
+ * `threshold` times the mean (default 1.3; 0 = never), all ranks re-plan equal-count cuts on the
+ * x-layer histogram of the whole scene.  Collective setting: the same value on every rank. */
+int pbf_slab_set_rebalance(pbf_ctx* ctx, float threshold);
+uint64_t pbf_slab_rebalance_count(const pbf_ctx* ctx);
 int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py,
                       float* pz, float* vx, float* vy, float* vz);
 /* Exchanges and bytes sent since creation, ghosts held after the last substep, migration hops. */

@@ -209,6 +209,8 @@ def test_virtual_slabs_rebalance(built):
     params, planes, state = _scene(scenes.SCENES["fluid_large"], H.STABLE_FLAGS, vx=2.0)
     sol = _single(params, planes, state)
     grp = SlabGroup([0] * 4, params, planes)
+    for s in grp.slabs:
+        s.set_rebalance(0.0)            # the automatic policy would have moved the cuts already
     grp.upload(state)
     grp.step(20)
     sol.step(20)
@@ -236,3 +238,29 @@ def test_virtual_slabs_fluid_million(built):
     sol.step(4)
     _assert_same(grp, sol, "fluid_million, 2 slabs, 4 substeps")
     grp.close()
+
+
+def test_virtual_slabs_automatic_rebalancing(built):
+    """The block drifts to +x: the left slabs empty, the right ones fill up.  With the automatic
+    policy the cuts follow (decided on every rank from the max-reduced status block, planned on an
+    all-reduced x-layer histogram); the result stays bit-identical to one GPU."""
+    params, planes, state = _scene(scenes.SCENES["fluid_large"], H.STABLE_FLAGS, vx=3.0)
+    sol = _single(params, planes, state)
+    counts = {}
+    for policy, threshold in (("off", 0.0), ("auto", 1.15)):
+        grp = SlabGroup([0] * 4, params, planes)
+        for s in grp.slabs:
+            s.set_rebalance(threshold)
+        grp.upload(state)
+        for _ in range(8):
+            grp.step(5)
+        counts[policy] = (grp.owned(), [s.rebalance_count() for s in grp.slabs])
+        if policy == "off":
+            sol.step(40)
+        _assert_same(grp, sol, f"rebalancing {policy}")
+        grp.close()
+    assert counts["off"][1] == [0, 0, 0, 0]
+    assert len(set(counts["auto"][1])) == 1 and counts["auto"][1][0] >= 1      # every slab took the same decisions
+    spread = lambda c: max(c) / (sum(c) / len(c))
+    assert spread(counts["auto"][0]) < spread(counts["off"][0])
+    assert spread(counts["auto"][0]) < 1.5
