@@ -230,12 +230,16 @@ def main():
     ap.add_argument("--flags", default="all")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--iterations", type=int, default=4)
+    ap.add_argument("--drift", type=float, default=0.0, help="initial x velocity of every particle (forces migration / re-balancing)")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank()
     params, planes, state = B.load_scene(args.scene, B.FLAGSETS[args.flags], args.iterations)
+    if args.drift:
+        state = [a.copy() for a in state]
+        state[3][:] = np.float32(args.drift)
     sol = make_slab(dist, local, params, planes, state, PBF_MODE_STRICT)
     sol.step(args.steps // 2)            # first batch: plain stream launches (NCCL warm-up)
     sol.step(args.steps - args.steps // 2)   # second batch: the captured CUDA graph, exchanges included
@@ -252,7 +256,8 @@ def main():
                if not np.array_equal(a.view(np.uint32), b.view(np.uint32))]
         ok = not bad
         print(f"slab check {'ok' if ok else 'FAILED ' + str(bad)}: {args.scene}, {dist.get_world_size()} slabs, "
-              f"{args.steps} substeps, stats {sol.slab_stats()}", flush=True)
+              f"{args.steps} substeps, stats {sol.slab_stats()}, re-balanced {sol.rebalance_count()}x, "
+              f"owned on rank 0: {sol.owned()}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     raise SystemExit(0 if ok else 1)
