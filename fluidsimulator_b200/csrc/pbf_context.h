@@ -89,11 +89,9 @@ struct SlabState {
   uint64_t bytes_sent = 0;
   uint64_t graph_exchanges = 0, graph_bytes = 0;  // per replay of the captured substep
   bool warm = false;                       // a batch has completed since the communicator was joined
-  bool fixed_caps = false;                 // keep the message capacities (no adaptive shrinking)
   float rebalance_threshold = 1.3f;        // re-plan the cuts when max / mean owned exceeds it (0 = never)
   uint64_t rebalances = 0;
   DevBuf<unsigned long long> hist_dev;     // x-layer histogram / staging of host all-reduces
-  int want_p2p = -1;                       // direct peer stores instead of messages: -1 = default for the transport
   Transport* transport = nullptr;          // not owned when it belongs to a group
   bool owns_transport = false;
   DevBuf<SlabCounts> counts;

@@ -844,15 +844,13 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       // Messages are sent at full capacity (their size is not known to the host), so capacities
       // follow the observed maxima down as well as up.  The maxima are max-reduced over the slabs:
       // every rank takes the same decision.
-      if (!sl.fixed_caps) {
-        const int want_g = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
-        const int want_m = (int)(st.max_send + st.max_send / 2 + 1024);
-        if (want_g < sl.gcap - sl.gcap / 4 || want_m < sl.mcap / 2) {
-          if (want_g < sl.gcap - sl.gcap / 4) sl.gcap = want_g;
-          if (want_m < sl.mcap / 2) sl.mcap = want_m;
-          sl.tot_cap = ctx->cap + 2 * (size_t)sl.gcap;
-          invalidate_graph(ctx);
-        }
+      const int want_g = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
+      const int want_m = (int)(st.max_send + st.max_send / 2 + 1024);
+      if (want_g < sl.gcap - sl.gcap / 4 || want_m < sl.mcap / 2) {
+        if (want_g < sl.gcap - sl.gcap / 4) sl.gcap = want_g;
+        if (want_m < sl.mcap / 2) sl.mcap = want_m;
+        sl.tot_cap = ctx->cap + 2 * (size_t)sl.gcap;
+        invalidate_graph(ctx);
       }
       return PBF_OK;
     }
@@ -1243,7 +1241,6 @@ int pbf_debug_set_slab_capacity(pbf_ctx* ctx, int mcap, int gcap) {
   if (!ctx || mcap < 1 || gcap < 1) return PBF_E_INVALID;
   ctx->slab.mcap = mcap;
   ctx->slab.gcap = gcap;
-  ctx->slab.fixed_caps = false;
   return PBF_OK;
 }
 
