@@ -63,3 +63,27 @@ def test_product_does_not_import_oracle():
         if path.suffix in {".py", ".cu", ".cuh", ".cpp", ".h", ".hpp"} or path.name == "Makefile":
             text = path.read_text(errors="ignore")
             assert "oracle_api" not in text and "oracle/" not in text and "pbf_oracle" not in text, path
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pbf_b200.h compiles as C11 (no C++-isms in the ABI) and a C program links the library."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text(
+        '#include "pbf_b200.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "  pbf_params p;\n"
+        "  pbf_default_params(&p);\n"
+        "  const char* err = 0;\n"
+        "  int n = pbf_device_count(&err);\n"
+        '  printf("abi %d iters %d devices %d\\n", pbf_abi_version(), (int)p.solver_iterations, n);\n'
+        "  return (pbf_abi_version() == PBF_ABI_VERSION && sizeof(pbf_params) == 23 * 4) ? 0 : 1;\n"
+        "}\n")
+    lib_dir = capi.LIB_PATH.parent
+    exe = tmp_path / "abi_check"
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src),
+                    "-o", str(exe), f"-L{lib_dir}", "-lpbf_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("abi 1 iters 4")
