@@ -153,6 +153,8 @@ int ensure_tables(pbf_ctx* ctx) {
   if (ctx->nbr_idx.n < need) {
     invalidate_graph(ctx);
     PBF_CUDA(ctx, ctx->nbr_idx.reserve(need));
+    // rows are only filled up to each particle's count; the debug surface copies whole rows
+    PBF_CUDA(ctx, cudaMemsetAsync(ctx->nbr_idx.p, 0, need * sizeof(uint32_t), ctx->stream));
   }
   if (ctx->debug) {
     PBF_CUDA(ctx, ctx->dbg_lambda.reserve(slots));
