@@ -72,6 +72,7 @@ struct SolveBuffers {
   float4* pred[2];   // ping-pong (pred xyz, lambda)
   float4* pos_s;     // (pos xyz, bits(orig id))
   float4* vel[2];    // (vel xyz, m/rho)
+  PosVel* pv;        // XSPH input record, written by the last delta pass instead of vel[0] when XSPH runs
   float4* omega;     // (omega xyz, |omega|)
   float* rho;
   const float4* planes;  // (nx, ny, nz, d) x nplanes, device
@@ -85,6 +86,7 @@ struct SolveBuffers {
 // a8..a14 for one substep: I x (lambda, delta), velocity update, XSPH, vorticity,
 // restitution, scatter to original order.  `strict` picks the arithmetic policy.
 // stage_cb (may be null) is invoked between stages for profiling.
+PosVel* xsph_record(const SolveBuffers& b, const StepConsts& c);  // b.pv when XSPH runs, else nullptr
 typedef void (*StageCallback)(void* user, int stage_id, int begin);
 int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c,
                  int iterations, NRef n, bool strict, cudaStream_t s,
@@ -143,7 +145,7 @@ int launch_slab_xrange(const float4* pos_o, const SlabBuffers& sb, const StepCon
 int launch_slab_xhist(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int x_min, int layers,
                       unsigned long long* hist, cudaStream_t s);
 // ghost velocities (pred - pos)/dt and m/rho, recomputed locally after the last pred refresh
-int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel,
+int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel, PosVel* pv,
                           const SlabBuffers& sb, const StepConsts& c, bool strict, cudaStream_t s);
 
 }  // namespace pbf

@@ -292,7 +292,8 @@ k_slab_halo_unpack(const float4* __restrict__ recv_l, const float4* __restrict__
 template <bool S>
 __global__ void __launch_bounds__(kThreads)
 k_slab_ghost_vel(const float4* __restrict__ pred, const float4* __restrict__ pos_s, const float* __restrict__ rho,
-                 float4* __restrict__ vel, const SlabCounts* __restrict__ counts, const StatusBlock* st, StepConsts c) {
+                 float4* __restrict__ vel, PosVel* __restrict__ pv, const SlabCounts* __restrict__ counts,
+                 const StatusBlock* st, StepConsts c) {
   pdl_wait();
   if (batch_failed(st)) return;
   const int i = counts->n_own + blockIdx.x * kThreads + threadIdx.x;
@@ -312,7 +313,13 @@ k_slab_ghost_vel(const float4* __restrict__ pred, const float4* __restrict__ pos
     vz = (q.z - p.z) * c.inv_dt;
     inv_rho = r > 0.0f ? c.mass / r : 0.0f;
   }
-  vel[i] = make_float4(vx, vy, vz, inv_rho);
+  const float4 v4 = make_float4(vx, vy, vz, inv_rho);
+  if (pv) {  // XSPH follows and gathers (pos, vel) records, see k_delta
+    pv[i].p = make_float4(q.x, q.y, q.z, 0.0f);
+    pv[i].v = v4;
+  } else {
+    vel[i] = v4;
+  }
 }
 
 // ---------------------------------------------------------------- re-balancing support
@@ -405,12 +412,12 @@ int launch_slab_xhist(const float4* pos_o, const SlabBuffers& sb, const StepCons
   return 1;
 }
 
-int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel,
+int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel, PosVel* pv,
                           const SlabBuffers& sb, const StepConsts& c, bool strict, cudaStream_t s) {
   if (strict)
-    PBF_LAUNCH(k_slab_ghost_vel<true>, grid_for(2 * sb.gcap), kThreads, s, pred_final, pos_s, rho, vel, sb.counts, sb.status, c);
+    PBF_LAUNCH(k_slab_ghost_vel<true>, grid_for(2 * sb.gcap), kThreads, s, pred_final, pos_s, rho, vel, pv, sb.counts, sb.status, c);
   else
-    PBF_LAUNCH(k_slab_ghost_vel<false>, grid_for(2 * sb.gcap), kThreads, s, pred_final, pos_s, rho, vel, sb.counts, sb.status, c);
+    PBF_LAUNCH(k_slab_ghost_vel<false>, grid_for(2 * sb.gcap), kThreads, s, pred_final, pos_s, rho, vel, pv, sb.counts, sb.status, c);
   return 1;
 }
 

@@ -112,10 +112,10 @@ __device__ __forceinline__ void for_each_pair(const uint32_t* __restrict__ nbr_i
   }
 }
 
-template <typename Body>
+// Same walk for the passes that need two float4 per neighbour; fetch(j, a, b) gathers them.
+template <typename Fetch, typename Body>
 __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_idx, int K, int i,
-                                               uint32_t cnt, const float4* __restrict__ a4,
-                                               const float4* __restrict__ b4, Body body) {
+                                               uint32_t cnt, Fetch fetch, Body body) {
   const uint2* row = reinterpret_cast<const uint2*>(nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u) + (i & 31);
   const uint32_t npairs = cnt >> 1;
   uint32_t p = 0;
@@ -136,10 +136,8 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
     }
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) {
-      a0[u] = a4[j[u].x];
-      a1[u] = a4[j[u].y];
-      b0[u] = b4[j[u].x];
-      b1[u] = b4[j[u].y];
+      fetch(j[u].x, a0[u], b0[u]);
+      fetch(j[u].y, a1[u], b1[u]);
     }
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], b0[u], b1[u], true);
@@ -152,10 +150,8 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
     for (int u = 0; u < kPairUnroll; ++u) j[u] = __ldcs(row + (size_t)(p + u) * 32u);
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) {
-      a0[u] = a4[j[u].x];
-      a1[u] = a4[j[u].y];
-      b0[u] = b4[j[u].x];
-      b1[u] = b4[j[u].y];
+      fetch(j[u].x, a0[u], b0[u]);
+      fetch(j[u].y, a1[u], b1[u]);
     }
 #pragma unroll
     for (int u = 0; u < kPairUnroll; ++u) body(a0[u], a1[u], b0[u], b1[u], true);
@@ -163,11 +159,17 @@ __device__ __forceinline__ void for_each_pair2(const uint32_t* __restrict__ nbr_
 #endif
   for (; p < npairs; ++p) {
     const uint2 j = __ldcs(row + (size_t)p * 32u);
-    body(a4[j.x], a4[j.y], b4[j.x], b4[j.y], true);
+    float4 a0, a1, b0, b1;
+    fetch(j.x, a0, b0);
+    fetch(j.y, a1, b1);
+    body(a0, a1, b0, b1, true);
   }
   if (cnt & 1u) {
     const uint32_t j = __ldcs(reinterpret_cast<const uint32_t*>(row + (size_t)npairs * 32u));
-    body(a4[j], a4[i], b4[j], b4[i], false);
+    float4 a0, a1, b0, b1;
+    fetch(j, a0, b0);
+    fetch((uint32_t)i, a1, b1);
+    body(a0, a1, b0, b1, false);
   }
 }
 
@@ -352,8 +354,9 @@ __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
         const float4* __restrict__ pos_s, const float* __restrict__ rho, float4* __restrict__ vel_out,
-        const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
-        StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final, int K, NRef nr) {
+        PosVel* __restrict__ pv, const float4* __restrict__ planes, float4* __restrict__ pos_o,
+        float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final,
+        int K, NRef nr) {
   pdl_wait();
   using M = M2<S>;
   using F = FT<S>;
@@ -426,7 +429,13 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
     } else {
       const F r(rho[i]);
       const F inv_rho = (r > F(0.0f)) ? (F(c.mass) / r) : F(0.0f);  // core.cpp:447-448
-      vel_out[i] = make_float4(Arith<F>::val(v.x), Arith<F>::val(v.y), Arith<F>::val(v.z), Arith<F>::val(inv_rho));
+      const float4 v4 = make_float4(Arith<F>::val(v.x), Arith<F>::val(v.y), Arith<F>::val(v.z), Arith<F>::val(inv_rho));
+      if (pv) {  // XSPH follows: it reads position and velocity of a neighbour as one 32-byte record
+        pv[i].p = np;
+        pv[i].v = v4;
+      } else {
+        vel_out[i] = v4;
+      }
     }
   }
 }
@@ -434,8 +443,8 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
 // ---------------------------------------------------------------- a12 XSPH
 template <bool S>
 __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
-k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4* __restrict__ vel_out,
-       const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
+k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, const PosVel* __restrict__ pv,
+       float4* __restrict__ vel_out, const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
        const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
        float4* __restrict__ vel_o, StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final,
        int K, NRef nr) {
@@ -446,12 +455,26 @@ k_xsph(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4
   const int n = nr.get();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+#if PBF_XSPH_PV
+  const float4 pi = pv[i].p;
+  const float4 vi = pv[i].v;
+  auto fetch = [&](uint32_t j, float4& a, float4& b) {
+    const PosVel r = ld_posvel(pv + j);
+    a = r.p;
+    b = r.v;
+  };
+#else
   const float4 pi = pos[i];
   const float4 vi = vel_in[i];
+  auto fetch = [&](uint32_t j, float4& a, float4& b) {
+    a = pos[j];
+    b = vel_in[j];
+  };
+#endif
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
   using A = A1<S>;
   const f2 pxy = make_float2(pi.x, pi.y), vxy = make_float2(vi.x, vi.y);
-  for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel_in,
+  for_each_pair2(nbr_idx, K, i, nbr_count[i], fetch,
                  [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v1) {
     const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
     f2 w = poly6_2<S, false>(make_float2(g0.r2, g1.r2), c);
@@ -511,7 +534,11 @@ k_vort_omega(float4* __restrict__ pos, const float4* __restrict__ vel, float4* _
     oy = M::adds(oy, ty);
     oz = M::adds(oz, tz);
   };
-  for_each_pair2(nbr_idx, K, i, nbr_count[i], pos, vel,
+  auto fetch = [&](uint32_t j, float4& a, float4& b) {
+    a = pos[j];
+    b = vel[j];
+  };
+  for_each_pair2(nbr_idx, K, i, nbr_count[i], fetch,
                  [&](float4 a0, float4 a1, float4 b0, float4 b1, bool v1) {
     const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
     f2 gf = spiky_2<S>(make_float2(g0.r2, g1.r2), c);
@@ -613,6 +640,16 @@ k_commit_only(const float4* __restrict__ pred, const float4* __restrict__ pos_s,
 // ---- per-pass launchers (the slab driver interleaves them with halo exchanges) ----------------
 static inline int blocks_for(NRef n) { return (n.n + kBlock - 1) / kBlock; }
 
+// Where the velocity update leaves (pos, vel, m/rho) for the pass after it: the 32-byte records
+// when that pass is XSPH, vel[0] otherwise (vorticity without XSPH).
+PosVel* xsph_record(const SolveBuffers& b, const StepConsts& c) {
+#if PBF_XSPH_PV
+  return c.do_xsph ? b.pv : nullptr;
+#else
+  return nullptr;
+#endif
+}
+
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
                   bool strict, cudaStream_t s, Span span) {
   // n.n bounds the thread count; with a span it is the caller's bound for that part
@@ -630,12 +667,12 @@ static void delta_impl(const SolveBuffers& b, const NeighborList& nl, const Step
                        bool is_final, NRef n, cudaStream_t s) {
   if (last)
     PBF_LAUNCH((k_delta<S, true>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                     b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo,
-                                                     is_final ? 1 : 0, nl.K, n);
+                                                     b.vel[0], xsph_record(b, c), b.planes, b.pos_o, b.vel_o, c, b.status,
+                                                     b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   else
     PBF_LAUNCH((k_delta<S, false>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                      b.vel[0], b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo, 0,
-                                                      nl.K, n);
+                                                      b.vel[0], (PosVel*)nullptr, b.planes, b.pos_o, b.vel_o, c, b.status,
+                                                      b.dbg, b.halo, 0, nl.K, n);
 }
 
 int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
@@ -648,11 +685,11 @@ int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts
 int launch_xsph(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,
                 NRef n, bool strict, cudaStream_t s) {
   if (strict)
-    PBF_LAUNCH(k_xsph<true>, blocks_for(n), kBlock, s, pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
-                                                 b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
+    PBF_LAUNCH(k_xsph<true>, blocks_for(n), kBlock, s, pos, b.vel[0], b.pv, b.vel[1], nl.idx, nl.count, b.pos_s, b.planes,
+                                                 b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   else
-    PBF_LAUNCH(k_xsph<false>, blocks_for(n), kBlock, s, pos, b.vel[0], b.vel[1], nl.idx, nl.count, b.pos_s, b.planes, b.pos_o,
-                                                  b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
+    PBF_LAUNCH(k_xsph<false>, blocks_for(n), kBlock, s, pos, b.vel[0], b.pv, b.vel[1], nl.idx, nl.count, b.pos_s, b.planes,
+                                                  b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
   return 1;
 }
 

@@ -117,6 +117,7 @@ int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep) {
   PBF_CUDA(ctx, ctx->pos_s.reserve(tot));
   PBF_CUDA(ctx, ctx->vel_a.reserve(tot));
   PBF_CUDA(ctx, ctx->vel_b.reserve(tot));
+  PBF_CUDA(ctx, ctx->pv.reserve(tot));
   PBF_CUDA(ctx, ctx->omega.reserve(tot));
   PBF_CUDA(ctx, ctx->rho.reserve(tot));
   PBF_CUDA(ctx, ctx->keys0.reserve(cap));
@@ -229,6 +230,7 @@ void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
   b.pos_s = ctx->pos_s.p;
   b.vel[0] = ctx->vel_a.p;
   b.vel[1] = ctx->vel_b.p;
+  b.pv = ctx->pv.p;
   b.omega = ctx->omega.p;
   b.rho = ctx->rho.p;
   b.planes = ctx->planes_dev.p;
@@ -437,7 +439,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   invalidate_graph(ctx);
   ctx->pos_o.release(); ctx->vel_o.release(); ctx->pos_bak.release(); ctx->vel_bak.release();
   ctx->pred_o.release(); ctx->pred_a.release(); ctx->pred_b.release(); ctx->pos_s.release();
-  ctx->vel_a.release(); ctx->vel_b.release(); ctx->omega.release(); ctx->rho.release();
+  ctx->vel_a.release(); ctx->vel_b.release(); ctx->pv.release(); ctx->omega.release(); ctx->rho.release();
   ctx->planes_dev.release(); ctx->desc.release(); ctx->status.release();
   ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
   ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release(); ctx->cell_key.release();

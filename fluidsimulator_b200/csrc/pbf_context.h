@@ -137,6 +137,7 @@ struct pbf_ctx {
   pbf::DevBuf<float4> pos_o, vel_o, pos_bak, vel_bak, pred_o;
   // sorted-order work arrays
   pbf::DevBuf<float4> pred_a, pred_b, pos_s, vel_a, vel_b, omega;
+  pbf::DevBuf<pbf::PosVel> pv;  // (pos, vel, m/rho) records gathered by XSPH
   pbf::DevBuf<float> rho;
   pbf::DevBuf<float4> planes_dev;
   // grid

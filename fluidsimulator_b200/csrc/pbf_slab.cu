@@ -623,7 +623,7 @@ int slab_substep(pbf_ctx* ctx) {
   if (final_in_delta) return launches;
 
   float4* pos = b.pred[cur];
-  launches += launch_slab_ghost_vel(pos, b.pos_s, b.rho, b.vel[0], sb, c, strict, s);
+  launches += launch_slab_ghost_vel(pos, b.pos_s, b.rho, b.vel[0], xsph_record(b, c), sb, c, strict, s);
   t.launches[PBF_STAGE_EXCHANGE] += 1;
   int vcur = 0;
   if (tail_xsph) {
