@@ -162,6 +162,7 @@ ABI = {
     "pbf_slab_upload_owned": (C.c_int, [C.c_void_p, C.c_size_t, _i64p] + [_f32p] * 6),
     "pbf_slab_set_p2p": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
+    "pbf_slab_plan_hist": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int, C.c_float, _i32p]),
     "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
     "pbf_slab_set_cuts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "pbf_slab_set_rebalance": (C.c_int, [C.c_void_p, C.c_float]),
@@ -351,6 +352,18 @@ def slab_plan(px: np.ndarray, h: float, nranks: int) -> np.ndarray:
     rc = lib.pbf_slab_plan(px.shape[0], fptr(px), C.c_float(h), nranks, iptr(cuts))
     if rc != 0:
         raise PbfError(f"pbf_slab_plan failed ({rc}): {(lib.pbf_last_error(None) or b'?').decode()}")
+    return cuts
+
+
+def slab_plan_hist(hist: np.ndarray, first_layer: int, nranks: int, ghost_weight: float) -> np.ndarray:
+    """pbf_slab_plan_hist: the planner on an x-layer histogram with an explicit ghost weight."""
+    lib = load_library()
+    hist = np.ascontiguousarray(hist, dtype=np.uint64)
+    cuts = np.empty(nranks + 1, dtype=np.int32)
+    rc = lib.pbf_slab_plan_hist(hist.ctypes.data_as(C.POINTER(C.c_uint64)), hist.shape[0], int(first_layer), nranks,
+                                C.c_float(ghost_weight), iptr(cuts))
+    if rc != 0:
+        raise PbfError(f"pbf_slab_plan_hist failed ({rc}): {(lib.pbf_last_error(None) or b'?').decode()}")
     return cuts
 
 

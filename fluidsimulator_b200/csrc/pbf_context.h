@@ -90,6 +90,7 @@ struct SlabState {
   uint64_t graph_exchanges = 0, graph_bytes = 0;  // per replay of the captured substep
   bool warm = false;                       // a batch has completed since the communicator was joined
   float rebalance_threshold = 1.3f;        // re-plan the cuts when max / mean owned exceeds it (0 = never)
+  double planned_ratio = 1.0;              // max / mean owned the last automatic plan produced by itself
   uint64_t rebalances = 0;
   DevBuf<unsigned long long> hist_dev;     // x-layer histogram / staging of host all-reduces
   Transport* transport = nullptr;          // not owned when it belongs to a group

@@ -31,16 +31,76 @@ inline int host_cell(float x, float inv_h) {
   return (int)f;
 }
 
-// Cuts on x-cell boundaries with (nearly) equal particle counts; every slab at least two cells
-// wide so that both ghost layers of a slab come from its direct neighbour.  hist[l] = particles in
-// the x-layer lo + l.
-int plan_cuts_hist(const std::vector<size_t>& hist, int lo, int nranks, std::vector<int>& cuts, std::string& err) {
+// ---- work-weighted cuts -------------------------------------------------------------------------
+// A slab does not only pay for the particles it owns: the first ghost layer on each interior side
+// gets neighbour lists and a lambda per iteration (about half the cost of an owned particle:
+// neighbours + lambda are ~50 % of a substep), the second layer is only copied.
+// Modelled cost of slab r owning layers [a, b):
+//     sum hist[a..b)  +  w * (g(a-1) + g(b))  +  w/4 * (g(a-2) + g(b+1))
+// with g(l) = hist[l] on a side that faces another slab and 0 at the two ends of the scene.  For
+// 0 <= w <= 1 the cost grows when the interval grows on either side.  Whether every slab can stay
+// under a bound T is decided by a sweep over the reachable cut positions (the >= 2 layers rule
+// rules out the plain greedy fill), and a binary search over T gives the cuts that minimise the
+// most expensive slab.  w = 0 balances owned particles only.  Costs are integers in units of
+// 1/256 particle.
+constexpr unsigned long long kCostUnit = 256;
+
+struct CutPlanner {
+  const std::vector<size_t>& hist;
+  const int nranks;
+  const long long layers;
+  unsigned long long w1, w2;               // ghost weights in 1/256
+  std::vector<unsigned long long> prefix;  // prefix[l] = particles in layers [0, l)
+
+  CutPlanner(const std::vector<size_t>& h, int r, float ghost_weight) : hist(h), nranks(r), layers((long long)h.size()) {
+    const float w = std::min(1.0f, std::max(0.0f, ghost_weight));
+    w1 = (unsigned long long)std::lround((double)w * (double)kCostUnit);
+    w2 = w1 / 4;
+    prefix.assign(hist.size() + 1, 0);
+    for (size_t l = 0; l < hist.size(); ++l) prefix[l + 1] = prefix[l] + hist[l];
+  }
+  unsigned long long at(long long l) const { return (l >= 0 && l < layers) ? (unsigned long long)hist[(size_t)l] : 0ull; }
+  // cost of slab r owning layers [a, b)
+  unsigned long long cost(int r, long long a, long long b) const {
+    unsigned long long c = (prefix[(size_t)b] - prefix[(size_t)a]) * kCostUnit;
+    if (r > 0) c += w1 * at(a - 1) + w2 * at(a - 2);
+    if (r < nranks - 1) c += w1 * at(b) + w2 * at(b + 1);
+    return c;
+  }
+  // reach[r][b] != 0: slabs 0..r can own the layers [0, b), each at least two layers wide and at
+  // most T expensive, with room for two layers per remaining slab (r = 0 .. nranks-2).  Returns
+  // whether the last slab can then take the rest.  For a fixed end the cheapest start of slab r is
+  // the LARGEST reachable one (cost shrinks with the interval), so one running maximum per slab
+  // decides every end: O(nranks * layers).
+  bool sweep(unsigned long long T, std::vector<std::vector<char>>& reach) const {
+    reach.assign((size_t)nranks - 1, std::vector<char>((size_t)layers + 1, 0));
+    for (int r = 0; r + 1 < nranks; ++r) {
+      const long long first = 2LL * (r + 1), last = layers - 2LL * (nranks - 1 - r);
+      long long start = (r == 0) ? 0 : -1;
+      for (long long b = first; b <= last; ++b) {
+        if (r > 0 && reach[(size_t)r - 1][(size_t)(b - 2)]) start = b - 2;
+        reach[(size_t)r][(size_t)b] = (start >= 0 && cost(r, start, b) <= T) ? 1 : 0;
+      }
+    }
+    for (long long a = layers - 2; a >= 2LL * (nranks - 1); --a)
+      if (reach[(size_t)nranks - 2][(size_t)a]) return cost(nranks - 1, a, layers) <= T;
+    return false;
+  }
+};
+
+// Cuts on x-cell boundaries that minimise the modelled cost of the most expensive slab; every slab
+// at least two cells wide so that both ghost layers of a slab come from its direct neighbour.
+// hist[l] = particles in the x-layer lo + l.  Among the plans that reach the optimum, each cut is
+// the one closest to its equal-share quantile, so that the cheaper slabs are balanced as well and
+// a re-plan on a slightly different histogram moves few layers.
+int plan_cuts_hist(const std::vector<size_t>& hist, int lo, int nranks, float ghost_weight, std::vector<int>& cuts,
+                   std::string& err) {
   cuts.assign((size_t)nranks + 1, 0);
   cuts[0] = INT_MIN;
   cuts[nranks] = INT_MAX;
   if (nranks == 1) return PBF_OK;
   const long long layers = (long long)hist.size();
-  size_t n = 0;
+  unsigned long long n = 0;
   for (size_t c : hist) n += c;
   if (n == 0 || layers < 2LL * nranks) {
     char buf[160];
@@ -49,20 +109,63 @@ int plan_cuts_hist(const std::vector<size_t>& hist, int lo, int nranks, std::vec
     err = buf;
     return PBF_E_INVALID;
   }
-  size_t cum = 0;
-  long long layer = 0;
-  for (int r = 1; r < nranks; ++r) {
-    const size_t target = (size_t)(((unsigned long long)n * (unsigned)r) / (unsigned)nranks);
-    const long long min_layer = (r == 1 ? 0 : (long long)cuts[r - 1] - lo) + 2;  // this slab >= 2 layers
-    const long long max_layer = layers - 2LL * (nranks - r);                      // room for the rest
-    while (layer < max_layer && (layer < min_layer || cum + hist[(size_t)layer] / 2 < target)) cum += hist[(size_t)layer++];
-    cuts[r] = (int)(lo + layer);
+  const CutPlanner pl(hist, nranks, ghost_weight);
+  std::vector<std::vector<char>> reach;
+  // owned and ghost layers of a slab are disjoint and every weight is <= 1: no slab costs more than n
+  unsigned long long lo_t = 0, hi_t = n * kCostUnit;
+  while (lo_t < hi_t) {
+    const unsigned long long mid = lo_t + (hi_t - lo_t) / 2;
+    if (pl.sweep(mid, reach)) hi_t = mid; else lo_t = mid + 1;
+  }
+  const unsigned long long T = hi_t;
+  if (!pl.sweep(T, reach)) {  // unreachable: T = n admits every plan of >= 2 layers per slab
+    err = "slab plan: internal error (no feasible plan)";
+    return PBF_E_INVALID;
+  }
+  // Walk back from the end: the start of slab r is any reachable cut that keeps the slab under T;
+  // take the one closest to the equal-share quantile n * r / nranks.
+  long long b = layers;
+  for (int r = nranks - 1; r >= 1; --r) {
+    const unsigned long long target = n * (unsigned)r;
+    long long pick = -1;
+    unsigned long long pick_dist = 0;
+    for (long long a = b - 2; a >= 2LL * r; --a) {
+      if (pl.cost(r, a, b) > T) break;  // cost only grows as the start moves left
+      if (!reach[(size_t)r - 1][(size_t)a]) continue;
+      const unsigned long long have = pl.prefix[(size_t)a] * (unsigned)nranks;
+      const unsigned long long dist = have > target ? have - target : target - have;
+      if (pick < 0 || dist < pick_dist) {
+        pick = a;
+        pick_dist = dist;
+      }
+    }
+    if (pick < 0) {
+      err = "slab plan: internal error (back-tracking lost the plan)";
+      return PBF_E_INVALID;
+    }
+    cuts[(size_t)r] = (int)(lo + pick);
+    b = pick;
   }
   return PBF_OK;
 }
 
+// Default ghost weight of every planner call of this process (environment PBF_SLAB_GHOST_WEIGHT,
+// 0 = balance owned particles only).
+float default_ghost_weight() {
+  static const float w = [] {
+    const char* e = std::getenv("PBF_SLAB_GHOST_WEIGHT");
+    if (e && *e) {
+      char* end = nullptr;
+      const float v = std::strtof(e, &end);
+      if (end != e && v >= 0.0f && v <= 1.0f) return v;
+    }
+    return 0.5f;
+  }();
+  return w;
+}
+
 int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& cuts, std::string& err) {
-  if (nranks == 1) return plan_cuts_hist({}, 0, 1, cuts, err);
+  if (nranks == 1) return plan_cuts_hist({}, 0, 1, 0.0f, cuts, err);
   if (n == 0) {
     err = "slab plan: no particles";
     return PBF_E_INVALID;
@@ -81,7 +184,7 @@ int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& 
   }
   std::vector<size_t> hist((size_t)layers, 0);
   for (size_t i = 0; i < n; ++i) hist[(size_t)(host_cell(px[i], inv_h) - lo)]++;
-  return plan_cuts_hist(hist, lo, nranks, cuts, err);
+  return plan_cuts_hist(hist, lo, nranks, default_ghost_weight(), cuts, err);
 }
 
 }  // namespace
@@ -683,7 +786,10 @@ int maybe_rebalance(pbf_ctx* ctx, const StatusBlock& st) {
     total += st.own_by_rank[r];
     largest = std::max<unsigned long long>(largest, st.own_by_rank[r]);
   }
-  if (total == 0 || (double)largest * sl.nranks <= (double)sl.rebalance_threshold * (double)total) return PBF_OK;
+  // planned_ratio: max / mean owned the last plan itself produced (> 1 when cell layers are coarse
+  // or the ghost weight gives the end slabs more) — only an imbalance beyond that is worth a re-plan
+  if (total == 0 || (double)largest * sl.nranks <= (double)sl.rebalance_threshold * sl.planned_ratio * (double)total)
+    return PBF_OK;
   SlabBuffers sb{};
   slab_fill(ctx, sb);
   // global x-cell range of the owned particles
@@ -715,11 +821,21 @@ int maybe_rebalance(pbf_ctx* ctx, const StatusBlock& st) {
   for (size_t l = 0; l < h.size(); ++l) h[l] = (size_t)hist[l];
   std::vector<int> cuts;
   std::string err;
-  if (plan_cuts_hist(h, (int)x_min, sl.nranks, cuts, err) != PBF_OK) return PBF_OK;  // can not do better: keep the cuts
+  if (plan_cuts_hist(h, (int)x_min, sl.nranks, default_ghost_weight(), cuts, err) != PBF_OK) return PBF_OK;  // can not do better: keep the cuts
+  unsigned long long planned_max = 0;
+  for (int r = 0; r < sl.nranks; ++r) {
+    const long long a = r == 0 ? 0 : (long long)cuts[(size_t)r] - x_min;
+    const long long b = r == sl.nranks - 1 ? layers : (long long)cuts[(size_t)r + 1] - x_min;
+    unsigned long long own = 0;
+    for (long long l = a; l < b; ++l) own += h[(size_t)l];
+    planned_max = std::max(planned_max, own);
+  }
+  sl.planned_ratio = std::max(1.0, (double)planned_max * sl.nranks / (double)total);
+  sl.rebalances++;  // the decision is global: every rank counts it, whether or not its own cuts move
+  if (cuts[(size_t)sl.rank] == sl.cut_lo && cuts[(size_t)sl.rank + 1] == sl.cut_hi) return PBF_OK;
   sl.cut_lo = cuts[(size_t)sl.rank];
   sl.cut_hi = cuts[(size_t)sl.rank + 1];
-  sl.rebalances++;
-  invalidate_graph(ctx);
+  invalidate_graph(ctx);  // the cuts are kernel parameters of the captured substep
   return PBF_OK;
 }
 
@@ -965,6 +1081,20 @@ int pbf_slab_plan(size_t n, const float* px, float h, int nranks, int32_t* cuts)
   std::vector<int> c;
   std::string err;
   const int rc = plan_cuts(n, px, h, nranks, c, err);
+  if (rc != PBF_OK) return fail(nullptr, rc, err);
+  for (int r = 0; r <= nranks; ++r) cuts[r] = c[(size_t)r];
+  return PBF_OK;
+}
+
+int pbf_slab_plan_hist(const uint64_t* hist, int32_t nlayers, int32_t first_layer, int nranks, float ghost_weight,
+                       int32_t* cuts) {
+  if (!cuts || nranks < 1 || nlayers < 0 || (nlayers > 0 && !hist) || !(ghost_weight >= 0.0f && ghost_weight <= 1.0f))
+    return fail(nullptr, PBF_E_INVALID, "pbf_slab_plan_hist: bad arguments");
+  std::vector<size_t> h((size_t)nlayers);
+  for (int32_t l = 0; l < nlayers; ++l) h[(size_t)l] = (size_t)hist[l];
+  std::vector<int> c;
+  std::string err;
+  const int rc = plan_cuts_hist(h, first_layer, nranks, ghost_weight, c, err);
   if (rc != PBF_OK) return fail(nullptr, rc, err);
   for (int r = 0; r <= nranks; ++r) cuts[r] = c[(size_t)r];
   return PBF_OK;

@@ -200,9 +200,16 @@ uint64_t pbf_launch_count(const pbf_ctx* ctx);
  * the ghosts once per solver iteration.  STRICT results are bit-identical to a single GPU. */
 
 /* Host-only planning: cuts[0..nranks] on x-cell boundaries (cuts[0] = INT32_MIN, cuts[nranks] =
- * INT32_MAX) with nearly equal particle counts and >= 2 cell layers per slab; slab r owns the
- * x-cells [cuts[r], cuts[r+1]).  Cell of a position: floor(x * (1.0f / h)) (core.cpp:28-34). */
+ * INT32_MAX) with >= 2 cell layers per slab; slab r owns the x-cells [cuts[r], cuts[r+1]).  Cell
+ * of a position: floor(x * (1.0f / h)) (core.cpp:28-34).  The cuts minimise the modelled work of
+ * the busiest slab: owned particles + ghost_weight * first ghost layers + ghost_weight / 4 *
+ * second ghost layers (slabs between two neighbours carry two ghost sides and therefore own
+ * fewer particles).  pbf_slab_plan, pbf_slab_upload and the automatic re-balancing use the
+ * process default (0.5, environment PBF_SLAB_GHOST_WEIGHT in [0, 1]; 0 = equal owned counts). */
 int pbf_slab_plan(size_t n, const float* px, float h, int nranks, int32_t* cuts);
+/* The same planner on a histogram: hist[l] = particles in the x-layer first_layer + l. */
+int pbf_slab_plan_hist(const uint64_t* hist, int32_t nlayers, int32_t first_layer, int nranks,
+                       float ghost_weight, int32_t* cuts);
 
 /* Multi-process transport: one NCCL communicator over the slabs.  It carries the halo messages
  * themselves (ncclSend/ncclRecv between x-neighbours) or, by default, only the cudaIpc handles of

@@ -53,6 +53,88 @@ def test_plan_uses_the_reference_cell_expression(built):
     assert cuts[1] == 4
 
 
+def _slab_costs(hist, cuts_rel, w):
+    """Modelled cost per slab (include/pbf_b200.h: owned + w * first ghost layers + w/4 * second),
+    in the planner's integer units of 1/256 particle."""
+    w1 = int(round(w * 256))
+    w2 = w1 // 4
+    L, R = len(hist), len(cuts_rel) - 1
+    at = lambda l: int(hist[l]) if 0 <= l < L else 0
+    out = []
+    for r in range(R):
+        a, b = cuts_rel[r], cuts_rel[r + 1]
+        c = 256 * int(np.sum(hist[a:b]))
+        if r > 0:
+            c += w1 * at(a - 1) + w2 * at(a - 2)
+        if r < R - 1:
+            c += w1 * at(b) + w2 * at(b + 1)
+        out.append(c)
+    return out
+
+
+def _brute_force_best(hist, nranks, w):
+    """Minimum over every valid plan (>= 2 layers per slab) of the busiest slab's cost."""
+    import itertools
+    L = len(hist)
+    best = None
+    for inner in itertools.combinations(range(2, L - 1), nranks - 1):
+        cuts = (0,) + inner + (L,)
+        if min(np.diff(cuts)) < 2:
+            continue
+        c = max(_slab_costs(hist, cuts, w))
+        best = c if best is None else min(best, c)
+    return best
+
+
+@pytest.mark.parametrize("w", [0.0, 0.25, 0.5, 1.0])
+def test_weighted_plan_is_optimal_on_small_histograms(built, w):
+    """The planner minimises the modelled cost of the busiest slab: checked against a brute-force
+    search over every valid plan on random histograms (uniform, piled-up, with empty layers)."""
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        L = int(rng.integers(4, 15))
+        nranks = int(rng.integers(2, min(4, L // 2) + 1))
+        kind = trial % 3
+        if kind == 0:
+            hist = rng.integers(50, 60, L)
+        elif kind == 1:
+            hist = (1000 * np.exp(-np.arange(L) / 3.0)).astype(np.int64) + rng.integers(0, 5, L)
+        else:
+            hist = rng.integers(0, 100, L) * rng.integers(0, 2, L)
+            hist[0] = hist[-1] = 1 + hist[0]
+        first = int(rng.integers(-50, 50))
+        cuts = capi.slab_plan_hist(hist, first, nranks, w)
+        assert cuts[0] == I32_MIN and cuts[-1] == I32_MAX
+        rel = [0] + [int(c) - first for c in cuts[1:-1]] + [L]
+        assert min(np.diff(rel)) >= 2, (hist, rel)
+        assert max(_slab_costs(hist, rel, w)) == _brute_force_best(hist, nranks, w), (hist, rel, w)
+
+
+def test_weighted_plan_gives_interior_slabs_fewer_particles(built):
+    """A uniform block of 58 layers over 8 slabs (7.25 layers each, about fluid_million on 8 GPUs):
+    the two 8-layer slabs go to the ends of the scene, which have one ghost side only, and the
+    modelled busiest slab is cheaper than with equal owned counts.  A ghost side weighs about one
+    cell layer, so this is all the model can change: one layer per slab."""
+    hist = np.full(58, 18_000, dtype=np.uint64)
+    equal = capi.slab_plan_hist(hist, 10, 8, 0.0)
+    weighted = capi.slab_plan_hist(hist, 10, 8, 0.5)
+    rel_e = [0] + [int(c) - 10 for c in equal[1:-1]] + [58]
+    rel_w = [0] + [int(c) - 10 for c in weighted[1:-1]] + [58]
+    assert np.diff(rel_w).tolist() == [8, 7, 7, 7, 7, 7, 7, 8]
+    assert sorted(np.diff(rel_e).tolist()) == [7] * 6 + [8] * 2       # w = 0: equal owned counts
+    assert max(_slab_costs(hist, rel_w, 0.5)) <= max(_slab_costs(hist, rel_e, 0.5))
+
+
+def test_plan_hist_rejects_bad_arguments(built):
+    with pytest.raises(capi.PbfError):
+        capi.slab_plan_hist(np.ones(8, dtype=np.uint64), 0, 2, 1.5)
+    with pytest.raises(capi.PbfError, match="can not be split"):
+        capi.slab_plan_hist(np.ones(3, dtype=np.uint64), 0, 2, 0.5)
+    with pytest.raises(capi.PbfError, match="can not be split"):
+        capi.slab_plan_hist(np.zeros(8, dtype=np.uint64), 0, 2, 0.5)   # no particles
+    assert capi.slab_plan_hist(np.zeros(0, dtype=np.uint64), 0, 1, 0.5).tolist() == [I32_MIN, I32_MAX]
+
+
 def test_two_gloo_ranks_split_and_gather():
     """world_size 2 on CPU: unique-id broadcast, ownership split and gather back to original order."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
