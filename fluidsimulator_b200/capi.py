@@ -475,7 +475,7 @@ class SlabGroup:
         return [s.owned() for s in self.slabs]
 
     def rebalance(self, h: float):
-        """New equal-count cuts from the current positions (pbf_slab_plan) on every slab."""
+        """New cuts from the current positions (pbf_slab_plan) on every slab."""
         px = self.download()[0]
         cuts = slab_plan(px, h, len(self.slabs))
         for r, s in enumerate(self.slabs):

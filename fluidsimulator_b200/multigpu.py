@@ -71,7 +71,7 @@ def gather_global(dist, gid: np.ndarray, state6, n_global: int, device):
 
 
 def rebalance(dist, sol: SlabSolver, h: float, device) -> np.ndarray:
-    """Collective: gathers the x coordinates of every slab, plans equal-count cuts on them
+    """Collective: gathers the x coordinates of every slab, plans new cuts on them
     (pbf_slab_plan — the same planner the upload uses) and installs them.  Misplaced particles
     migrate during the next substep; results do not depend on the cuts."""
     import torch
