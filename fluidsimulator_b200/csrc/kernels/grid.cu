@@ -426,6 +426,75 @@ __device__ __forceinline__ void neighbors_cell(const float4* __restrict__ pred_s
   }
 }
 
+// PBF_NBR_MASK=1: the candidate test and the list store are separated.  In the loop above some lane
+// of the warp has a hit in almost every step, so the whole warp walks through both store blocks
+// (62 instructions per candidate pair, 40 of them bookkeeping and control flow; SASS of r01e).  Here
+// the test loop only collects a bit per candidate (<= 32 candidates per chunk of a cell) and has no
+// hit-dependent control flow; the hits are then emitted from the mask in ascending slot order —
+// the order of the loop above, so the list is the same, entry for entry.
+// The second candidate of a step is loaded unconditionally: the slot after the last particle is
+// padding (ensure_particles) and its bit is masked.
+#ifndef PBF_NBR_MASK
+#define PBF_NBR_MASK 0
+#endif
+#ifndef PBF_NBR_HOIST
+#define PBF_NBR_HOIST 0
+#endif
+#ifndef PBF_NBR_MASK_UNROLL
+#define PBF_NBR_MASK_UNROLL 2
+#endif
+constexpr int kNbrMaskUnroll = PBF_NBR_MASK_UNROLL;  // candidate PAIRS per unrolled step of the test loop
+
+// List cursor of the mask variant: a pointer to the next entry instead of an element offset (two
+// instructions per hit for the address instead of four).
+struct NbrCursor {
+  uint32_t* p;    // entry `cnt` of this lane's list
+  uint32_t cnt;
+  uint32_t K;
+  __device__ __forceinline__ void put(int j) {
+    const uint32_t odd = cnt & 1u;
+    if (cnt < K) __stcs(p, (uint32_t)j);
+    p += 1u + 62u * odd;  // entry k at (k / 2) * 64 + k % 2
+    cnt += 1u;
+  }
+};
+
+template <bool CENTER>
+__device__ __forceinline__ void neighbors_cell_mask(const float4* __restrict__ pred_s, int2 range, float pz, f2 pxy,
+                                                    int i, float h2, NbrCursor& e) {
+#pragma unroll 1
+  for (int base = range.x; base < range.y; base += 32) {
+    const int end = min(range.y, base + 32);
+    uint32_t m = 0;
+#pragma unroll kNbrMaskUnroll
+    for (int j = base; j < end; j += 2) {
+      const float4 a0 = pred_s[j];
+      const float4 a1 = pred_s[j + 1];
+      const f2 d0 = __fadd2_rn(pxy, make_float2(-a0.x, -a0.y));
+      const f2 d1 = __fadd2_rn(pxy, make_float2(-a1.x, -a1.y));
+      const float z0 = __fsub_rn(pz, a0.z), z1 = __fsub_rn(pz, a1.z);
+      const f2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
+      const float r2a = __fadd_rn(__fadd_rn(q0.x, q0.y), __fmul_rn(z0, z0));
+      const float r2b = __fadd_rn(__fadd_rn(q1.x, q1.y), __fmul_rn(z1, z1));
+      // hits are shifted in from the top, two per step (core.cpp:231-240: strict r2 < h2)
+      m = (m >> 2) | ((r2a < h2) ? 0x40000000u : 0u) | ((r2b < h2) ? 0x80000000u : 0u);
+    }
+    const int lim = 32 - (end - base);            // 0 .. 31
+    m >>= lim & ~1;                               // candidate base + t at bit t (an odd chunk ran one slot over)
+    m &= 0xffffffffu >> lim;                      // ... whose bit is dropped here
+    if (CENTER) {
+      const uint32_t self = (uint32_t)(i - base);
+      if (self < 32u) m &= ~(1u << self);
+    }
+#pragma unroll 1
+    while (m) {
+      const int t = __ffs((int)m) - 1;
+      m &= m - 1u;
+      e.put(base + t);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
             const GridDesc* __restrict__ desc, const unsigned long long* __restrict__ cell_key,
@@ -452,11 +521,28 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
     if (!active) nbr_count[i] = 0;
   }
   if (active) {
+#if PBF_NBR_MASK
+    NbrCursor e;
+    e.p = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
+    e.cnt = 0;
+    e.K = (uint32_t)K;
+#if PBF_NBR_HOIST
+    // keep h2 in a register: ptxas otherwise re-loads it from the constant bank in every step of
+    // the test loop (1 of 27 issue slots).  blockIdx.x >> 31 is 0 and x + 0.0f == x for x > 0.
+    // (The same trick on the pred_s pointer makes ptxas rebuild the address with 4 instructions.)
+    const float4* const ps = pred_s;
+    const float h2r = __fadd_rn(h2, __uint_as_float(blockIdx.x >> 31));
+#else
+    const float4* const ps = pred_s;
+    const float h2r = h2;
+#endif
+#else
     NbrEmit e;
     e.out = nbr_idx + (size_t)(i >> 5) * (size_t)K * 32u + (uint32_t)(i & 31) * 2u;
     e.cnt = 0;
     e.off = 0;
     e.K = (uint32_t)K;
+#endif
     const uint32_t xstride = (uint32_t)dimy * (uint32_t)dimz;
     const bool sparse = desc->sparse != 0;
     const uint32_t mask = desc->ncells - 1u;
@@ -477,12 +563,21 @@ k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_ran
           r1 = cell_range[row + xstride];
           r2 = cell_range[row + 2u * xstride];
         }
+#if PBF_NBR_MASK
+        neighbors_cell_mask<false>(ps, r0, pi.z, pxy, i, h2r, e);
+        if (dz == 0 && dy == 0)
+          neighbors_cell_mask<true>(ps, r1, pi.z, pxy, i, h2r, e);
+        else
+          neighbors_cell_mask<false>(ps, r1, pi.z, pxy, i, h2r, e);
+        neighbors_cell_mask<false>(ps, r2, pi.z, pxy, i, h2r, e);
+#else
         neighbors_cell<false>(pred_s, r0, pi, pxy, i, h2, e);
         if (dz == 0 && dy == 0)
           neighbors_cell<true>(pred_s, r1, pi, pxy, i, h2, e);
         else
           neighbors_cell<false>(pred_s, r1, pi, pxy, i, h2, e);
         neighbors_cell<false>(pred_s, r2, pi, pxy, i, h2, e);
+#endif
       }
     cnt = e.cnt;
     nbr_count[i] = cnt < (uint32_t)K ? cnt : (uint32_t)K;

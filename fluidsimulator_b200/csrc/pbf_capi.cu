@@ -112,8 +112,9 @@ int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep) {
   PBF_CUDA(ctx, ctx->pos_bak.grow_keep(cap, keep));
   PBF_CUDA(ctx, ctx->vel_bak.grow_keep(cap, keep));
   PBF_CUDA(ctx, ctx->pred_o.reserve(cap));
-  PBF_CUDA(ctx, ctx->pred_a.reserve(tot));
-  PBF_CUDA(ctx, ctx->pred_b.reserve(tot));
+  // + 2: the neighbour kernel may load (and ignore) the slot after the last particle
+  PBF_CUDA(ctx, ctx->pred_a.reserve(tot + 2));
+  PBF_CUDA(ctx, ctx->pred_b.reserve(tot + 2));
   PBF_CUDA(ctx, ctx->pos_s.reserve(tot));
   PBF_CUDA(ctx, ctx->vel_a.reserve(tot));
   PBF_CUDA(ctx, ctx->vel_b.reserve(tot));
