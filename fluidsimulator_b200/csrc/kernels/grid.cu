@@ -435,13 +435,13 @@ __device__ __forceinline__ void neighbors_cell(const float4* __restrict__ pred_s
 // The second candidate of a step is loaded unconditionally: the slot after the last particle is
 // padding (ensure_particles) and its bit is masked.
 #ifndef PBF_NBR_MASK
-#define PBF_NBR_MASK 0
+#define PBF_NBR_MASK 1
 #endif
 #ifndef PBF_NBR_HOIST
-#define PBF_NBR_HOIST 0
+#define PBF_NBR_HOIST 1
 #endif
 #ifndef PBF_NBR_MASK_UNROLL
-#define PBF_NBR_MASK_UNROLL 2
+#define PBF_NBR_MASK_UNROLL 1
 #endif
 constexpr int kNbrMaskUnroll = PBF_NBR_MASK_UNROLL;  // candidate PAIRS per unrolled step of the test loop
 
@@ -495,7 +495,13 @@ __device__ __forceinline__ void neighbors_cell_mask(const float4* __restrict__ p
   }
 }
 
+// (an explicit minimum of 1 block per SM is not the same as none: ptxas then takes 52 registers
+// instead of 40)
+#ifdef PBF_NBR_MINBLOCKS
+__global__ void __launch_bounds__(128, PBF_NBR_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(128)
+#endif
 k_neighbors(const float4* __restrict__ pred_s, const int2* __restrict__ cell_range,
             const GridDesc* __restrict__ desc, const unsigned long long* __restrict__ cell_key,
             uint32_t* __restrict__ nbr_idx, uint32_t* __restrict__ nbr_count, StatusBlock* st, float inv_h, float h2,
