@@ -225,11 +225,13 @@ __device__ __forceinline__ f2 poly6_2(f2 r2, const StepConsts& c) {
 // can then only trigger through rounding at r2 ~ h2, and max(diff, 0) reproduces it up to the
 // sign of a zero that is added to an accumulator (x + -0 == x + +0 for every x but -0, and the
 // accumulators start at +0 and can never become -0).
-template <bool S>
+// SAFE: the host guarantees c.sqrt_safe (the launcher picked the specialised kernel), so the
+// choice between the two sqrt paths is not re-made for every neighbour pair.
+template <bool S, bool SAFE = false>
 __device__ __forceinline__ f2 spiky_2(f2 r2, const StepConsts& c) {
   using M = M2<S>;
   const f2 rc = make_float2(fmaxf(r2.x, c.min_r2), fmaxf(r2.y, c.min_r2));
-  const f2 r = M::sqrt(rc, c.sqrt_safe != 0);
+  const f2 r = M::sqrt(rc, SAFE || c.sqrt_safe != 0);
   f2 diff = M::sub(bcast(c.h), r);
   diff = make_float2(fmaxf(diff.x, 0.0f), fmaxf(diff.y, 0.0f));
   return M::mul(M::mul(bcast(c.spiky_coeff), diff), diff);
@@ -277,8 +279,18 @@ __device__ __forceinline__ void finalize_particle(float4 pos, V3<F> v, uint32_t 
 }
 
 // ---------------------------------------------------------------- a8 lambda
-template <bool S>
-__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
+// COMMON (both solver kernels): specialised for what every shipped scene uses — min_r2 and h2 inside
+// the fast-path range of the 2-wide sqrt, and s_corr off or with exponent 4 (core.h:33) — so that
+// neither the sqrt path nor the exponent is selected per neighbour pair, and the powf fallback of
+// pow_ratio_2 is not part of the loop body.  Same arithmetic; the launcher decides.
+// 9 blocks of 128 threads per SM = at most 56 registers: what the generic STRICT kernel takes by
+// itself (ptxas gives the specialised one 60 -> 8 blocks; the pass needs the warps to hide the
+// gathers).
+#ifndef PBF_LAMBDA_MINBLOCKS
+#define PBF_LAMBDA_MINBLOCKS 9
+#endif
+template <bool S, bool COMMON>
+__global__ void __launch_bounds__(kBlock, COMMON ? PBF_LAMBDA_MINBLOCKS : PBF_SOLVE_MINBLOCKS)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
          const StatusBlock* st, DebugPtrs dbg, Span span, int K, NRef nr) {
@@ -297,7 +309,7 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
     const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
     const f2 r2 = make_float2(g0.r2, g1.r2);
     f2 w = poly6_2<S, true>(r2, c);                        // rho += poly6(r2) (core.cpp:300)
-    f2 gf = spiky_2<S>(r2, c);
+    f2 gf = spiky_2<S, COMMON>(r2, c);
     // Straight-line code instead of two divergent branches: a neighbour that fails r2 < h2
     // (core.cpp:302) gets grad_factor = 0, so every term it adds below is a +-0 — a no-op on
     // accumulators that start at +0 (they can never hold -0).  Same for the odd tail slot.
@@ -349,7 +361,7 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
 
 // ---------------------------------------------------------------- a9 + a10 (+ a11, a14)
 // LAST: also velocity update / commit; is_final: additionally restitution + scatter.
-template <bool S, bool LAST>
+template <bool S, bool LAST, bool COMMON>
 __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
         const uint32_t* __restrict__ nbr_idx, const uint32_t* __restrict__ nbr_count,
@@ -371,12 +383,12 @@ k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
   for_each_pair(nbr_idx, K, i, nbr_count[i], pred_in, [&](float4 a0, float4 a1, bool v1) {
     const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
     const f2 r2 = make_float2(g0.r2, g1.r2);
-    const f2 gf = spiky_2<S>(r2, c);
+    const f2 gf = spiky_2<S, COMMON>(r2, c);
     f2 s = make_float2(A::add(pi.w, a0.w), A::add(pi.w, a1.w));  // lambda_i + lambda_j (core.cpp:355)
     if (c.scorr_on) {                                      // core.cpp:356-361
       const f2 w = poly6_2<S, false>(r2, c);
       const f2 ratio = M::mul(w, bcast(c.scorr_inv_wdq));
-      const f2 corr = M::mul(bcast(c.scorr_negk), pow_ratio_2<S>(ratio, c.scorr_n));
+      const f2 corr = M::mul(bcast(c.scorr_negk), pow_ratio_2<S>(ratio, COMMON ? 4 : c.scorr_n));
       s = M::addp(s, corr);
     }
     f2 sg = M::mul(s, gf);                                 // (s * grad_factor) * d (core.cpp:362-364)
@@ -650,35 +662,46 @@ PosVel* xsph_record(const SolveBuffers& b, const StepConsts& c) {
 #endif
 }
 
+// The specialised (COMMON) solver kernels apply: see k_lambda.  PBF_SOLVE_COMMON=0 builds without them.
+#ifndef PBF_SOLVE_COMMON
+#define PBF_SOLVE_COMMON 1
+#endif
+static inline bool common_case(const StepConsts& c) {
+  return PBF_SOLVE_COMMON && c.sqrt_safe != 0 && (c.scorr_on == 0 || c.scorr_n == 4);
+}
+
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
                   bool strict, cudaStream_t s, Span span) {
   // n.n bounds the thread count; with a span it is the caller's bound for that part
-  if (strict)
-    PBF_LAUNCH(k_lambda<true>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, span,
-               nl.K, n);
+  if (strict && common_case(c))
+    PBF_LAUNCH((k_lambda<true, true>), blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg,
+               span, nl.K, n);
+  else if (strict)
+    PBF_LAUNCH((k_lambda<true, false>), blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg,
+               span, nl.K, n);
   else
-    PBF_LAUNCH(k_lambda<false>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, span,
-               nl.K, n);
+    PBF_LAUNCH((k_lambda<false, false>), blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg,
+               span, nl.K, n);
   return 1;
 }
 
-template <bool S>
+template <bool S, bool COMMON>
 static void delta_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
                        bool is_final, NRef n, cudaStream_t s) {
   if (last)
-    PBF_LAUNCH((k_delta<S, true>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                     b.vel[0], xsph_record(b, c), b.planes, b.pos_o, b.vel_o, c, b.status,
-                                                     b.dbg, b.halo, is_final ? 1 : 0, nl.K, n);
+    PBF_LAUNCH((k_delta<S, true, COMMON>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s,
+               b.rho, b.vel[0], xsph_record(b, c), b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo,
+               is_final ? 1 : 0, nl.K, n);
   else
-    PBF_LAUNCH((k_delta<S, false>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s, b.rho,
-                                                      b.vel[0], (PosVel*)nullptr, b.planes, b.pos_o, b.vel_o, c, b.status,
-                                                      b.dbg, b.halo, 0, nl.K, n);
+    PBF_LAUNCH((k_delta<S, false, COMMON>), blocks_for(n), kBlock, s, b.pred[cur], b.pred[cur ^ 1], nl.idx, nl.count, b.pos_s,
+               b.rho, b.vel[0], (PosVel*)nullptr, b.planes, b.pos_o, b.vel_o, c, b.status, b.dbg, b.halo, 0, nl.K, n);
 }
 
 int launch_delta(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
                  bool is_final, NRef n, bool strict, cudaStream_t s) {
-  if (strict) delta_impl<true>(b, nl, c, cur, last, is_final, n, s);
-  else delta_impl<false>(b, nl, c, cur, last, is_final, n, s);
+  if (strict && common_case(c)) delta_impl<true, true>(b, nl, c, cur, last, is_final, n, s);
+  else if (strict) delta_impl<true, false>(b, nl, c, cur, last, is_final, n, s);
+  else delta_impl<false, false>(b, nl, c, cur, last, is_final, n, s);
   return 1;
 }
 
