@@ -279,18 +279,8 @@ __device__ __forceinline__ void finalize_particle(float4 pos, V3<F> v, uint32_t 
 }
 
 // ---------------------------------------------------------------- a8 lambda
-// COMMON (both solver kernels): specialised for what every shipped scene uses — min_r2 and h2 inside
-// the fast-path range of the 2-wide sqrt, and s_corr off or with exponent 4 (core.h:33) — so that
-// neither the sqrt path nor the exponent is selected per neighbour pair, and the powf fallback of
-// pow_ratio_2 is not part of the loop body.  Same arithmetic; the launcher decides.
-// 9 blocks of 128 threads per SM = at most 56 registers: what the generic STRICT kernel takes by
-// itself (ptxas gives the specialised one 60 -> 8 blocks; the pass needs the warps to hide the
-// gathers).
-#ifndef PBF_LAMBDA_MINBLOCKS
-#define PBF_LAMBDA_MINBLOCKS 9
-#endif
-template <bool S, bool COMMON>
-__global__ void __launch_bounds__(kBlock, COMMON ? PBF_LAMBDA_MINBLOCKS : PBF_SOLVE_MINBLOCKS)
+template <bool S>
+__global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
          const uint32_t* __restrict__ nbr_count, float* __restrict__ rho_out, StepConsts c,
          const StatusBlock* st, DebugPtrs dbg, Span span, int K, NRef nr) {
@@ -309,7 +299,7 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
     const NGeom g0 = ngeom<S>(pxy, pi.z, a0), g1 = ngeom<S>(pxy, pi.z, a1);
     const f2 r2 = make_float2(g0.r2, g1.r2);
     f2 w = poly6_2<S, true>(r2, c);                        // rho += poly6(r2) (core.cpp:300)
-    f2 gf = spiky_2<S, COMMON>(r2, c);
+    f2 gf = spiky_2<S>(r2, c);
     // Straight-line code instead of two divergent branches: a neighbour that fails r2 < h2
     // (core.cpp:302) gets grad_factor = 0, so every term it adds below is a +-0 — a no-op on
     // accumulators that start at +0 (they can never hold -0).  Same for the odd tail slot.
@@ -361,6 +351,12 @@ k_lambda(float4* __restrict__ pred, const uint32_t* __restrict__ nbr_idx,
 
 // ---------------------------------------------------------------- a9 + a10 (+ a11, a14)
 // LAST: also velocity update / commit; is_final: additionally restitution + scatter.
+// COMMON: specialised for what every shipped scene uses — min_r2 and h2 inside the fast-path range
+// of the 2-wide sqrt, and s_corr off or with exponent 4 (core.h:33) — so that neither the sqrt path
+// nor the exponent is selected per neighbour pair and the powf fallback of pow_ratio_2 is not part
+// of the loop body (664 instead of 1464 instructions).  Same arithmetic; the launcher decides.
+// MEASURED on B200 (fluid_million, settled): 76.7 -> 70.7 us per launch.  The same specialisation of
+// k_lambda was slower (68.1 -> 72.6 us at the 56 registers of the generic kernel) and is not used.
 template <bool S, bool LAST, bool COMMON>
 __global__ void __launch_bounds__(kBlock, PBF_SOLVE_MINBLOCKS)
 k_delta(const float4* __restrict__ pred_in, float4* __restrict__ pred_out,
@@ -662,7 +658,7 @@ PosVel* xsph_record(const SolveBuffers& b, const StepConsts& c) {
 #endif
 }
 
-// The specialised (COMMON) solver kernels apply: see k_lambda.  PBF_SOLVE_COMMON=0 builds without them.
+// The specialised (COMMON) delta kernels apply: see k_delta.  PBF_SOLVE_COMMON=0 builds without them.
 #ifndef PBF_SOLVE_COMMON
 #define PBF_SOLVE_COMMON 1
 #endif
@@ -673,15 +669,12 @@ static inline bool common_case(const StepConsts& c) {
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,
                   bool strict, cudaStream_t s, Span span) {
   // n.n bounds the thread count; with a span it is the caller's bound for that part
-  if (strict && common_case(c))
-    PBF_LAUNCH((k_lambda<true, true>), blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg,
-               span, nl.K, n);
-  else if (strict)
-    PBF_LAUNCH((k_lambda<true, false>), blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg,
-               span, nl.K, n);
+  if (strict)
+    PBF_LAUNCH(k_lambda<true>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, span,
+               nl.K, n);
   else
-    PBF_LAUNCH((k_lambda<false, false>), blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg,
-               span, nl.K, n);
+    PBF_LAUNCH(k_lambda<false>, blocks_for(n), kBlock, s, b.pred[cur], nl.idx, nl.count, b.rho, c, b.status, b.dbg, span,
+               nl.K, n);
   return 1;
 }
 
