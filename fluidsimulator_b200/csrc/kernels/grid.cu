@@ -385,11 +385,23 @@ k_cell_order(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slo
 // idx[(i/32)*K*32 + (k/2)*64 + (i%32)*2 + k%2]: a solver pass reads two entries per lane
 // with one 8-byte load, 256 contiguous bytes per warp.
 // The kernel is issue-bound (73 % issue-active, 19 of 32 lanes busy on average: lanes of a warp
-// sit in ~5 different cells whose stencil cells hold different numbers of particles).  The hit
-// path is kept short — a running element offset instead of re-deriving the list address, and only
-// the centre cell pays for the j != i test.  Three restructurings that remove the divergence
-// (flattened walk, warp per cell, tests in memory order + bitmasks) were measured and are slower,
-// see DESIGN.md §4.
+// sit in ~5 different cells whose stencil cells hold different numbers of particles).  Three
+// restructurings that remove the divergence (flattened walk, warp per cell, tests in memory order
+// + bitmasks) were measured and are slower, see DESIGN.md §4.
+//
+// Two per-cell loops exist.  neighbors_cell (PBF_NBR_MASK=0, kept for A/B runs) tests a pair of
+// candidates and stores the hits inside the same loop; neighbors_cell_mask (the default) first
+// collects the hits of a cell in a bit mask and then emits them.  Same list, entry for entry.
+#ifndef PBF_NBR_MASK
+#define PBF_NBR_MASK 1
+#endif
+#ifndef PBF_NBR_HOIST
+#define PBF_NBR_HOIST 1
+#endif
+#ifndef PBF_NBR_MASK_UNROLL
+#define PBF_NBR_MASK_UNROLL 1
+#endif
+#if !PBF_NBR_MASK
 struct NbrEmit {
   uint32_t* out;
   uint32_t cnt, off;  // entries so far; element offset of entry `cnt`: (cnt / 2) * 64 + cnt % 2
@@ -425,24 +437,18 @@ __device__ __forceinline__ void neighbors_cell(const float4* __restrict__ pred_s
     e.put(h1, j + 1);
   }
 }
+#endif
 
-// PBF_NBR_MASK=1: the candidate test and the list store are separated.  In the loop above some lane
-// of the warp has a hit in almost every step, so the whole warp walks through both store blocks
-// (62 instructions per candidate pair, 40 of them bookkeeping and control flow; SASS of r01e).  Here
-// the test loop only collects a bit per candidate (<= 32 candidates per chunk of a cell) and has no
-// hit-dependent control flow; the hits are then emitted from the mask in ascending slot order —
-// the order of the loop above, so the list is the same, entry for entry.
+// PBF_NBR_MASK=1 (default): the candidate test and the list store are separated.  In the loop above
+// some lane of the warp has a hit in almost every step, so the whole warp walks through both store
+// blocks (62 instructions per candidate pair, 40 of them bookkeeping and control flow; SASS of
+// r01e).  Here the test loop only collects a bit per candidate (<= 32 candidates per chunk of a
+// cell: 25 instructions per pair) and has no hit-dependent control flow; the hits are then emitted
+// from the mask in ascending slot order (17 instructions per hit) — the order of the loop above.
 // The second candidate of a step is loaded unconditionally: the slot after the last particle is
 // padding (ensure_particles) and its bit is masked.
-#ifndef PBF_NBR_MASK
-#define PBF_NBR_MASK 1
-#endif
-#ifndef PBF_NBR_HOIST
-#define PBF_NBR_HOIST 1
-#endif
-#ifndef PBF_NBR_MASK_UNROLL
-#define PBF_NBR_MASK_UNROLL 1
-#endif
+// MEASURED on B200 (fluid_million, settled, profiles/ab_r01g_*.txt): 254 -> 228 us, bit-identical
+// state and lists; unrolling the test loop 2x / 4x (48 / 56 registers) gives the gain back.
 constexpr int kNbrMaskUnroll = PBF_NBR_MASK_UNROLL;  // candidate PAIRS per unrolled step of the test loop
 
 // List cursor of the mask variant: a pointer to the next entry instead of an element offset (two
