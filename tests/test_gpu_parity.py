@@ -206,6 +206,33 @@ def test_fluid_million_properties(built):
         assert H.bit_equal(a, b)
 
 
+def test_fluid_million_matches_the_reference_digests(built):
+    """BASELINE.json's headline workload at full size against the reference itself: 1 000 000
+    particles, stable flags, free-running; the state after 65 and 280 substeps must hash to what
+    the unmodified reference CPU solver produced (tests/golden/million.json, written by
+    tests/golden/make_golden_million.py — a 15-minute CPU run, so the digests are committed)."""
+    import json
+    from fluidsimulator_b200.capi import Solver
+    path = G.GOLDEN / "million.json"
+    if not path.exists():
+        pytest.skip("tests/golden/million.json not generated")
+    gold = json.loads(path.read_text())
+    params, planes, state = scenes.load_scene(scenes.SCENES["fluid_million"])
+    params = H.configure(params, H.STABLE_FLAGS)
+    assert len(state[0]) == gold["particles"]
+    sol = Solver(0, len(state[0]))
+    sol.set_params(params)
+    sol.set_planes(planes)
+    sol.upload(state)
+    done = 0
+    for step in sorted(int(k) for k in gold["steps"]):
+        sol.step(step - done)
+        done = step
+        got = {name: G.digest(a) for name, a in zip(G.STATE, sol.download())}
+        bad = [name for name in G.STATE if got[name] != gold["steps"][str(step)][name]]
+        assert bad == [], f"substep {step}: {bad} differ from the reference"
+
+
 def test_strict_follows_the_reference_through_its_blow_up(built):
     """With vorticity on the reference diverges: within ~15 substeps particles fly
     kilometres away and the bounding box of occupied cells no longer fits a dense table.  The
