@@ -206,19 +206,25 @@ def test_fluid_million_properties(built):
         assert H.bit_equal(a, b)
 
 
-def test_fluid_million_matches_the_reference_digests(built):
-    """BASELINE.json's headline workload at full size against the reference itself: 1 000 000
-    particles, stable flags, free-running; the state after 65 and 280 substeps must hash to what
-    the unmodified reference CPU solver produced (tests/golden/million.json, written by
-    tests/golden/make_golden_million.py — a 15-minute CPU run, so the digests are committed)."""
+@pytest.mark.parametrize("run", ["fluid_million:stable", "fluid_million:all", "block_16m:stable"])
+def test_full_size_runs_match_the_reference_digests(built, run):
+    """The workloads bench.py measures, at full size, against the reference itself: free-running
+    state after N substeps must hash to what the unmodified reference CPU solver produced
+    (tests/golden/million.json, written by tests/golden/make_golden_million.py — a 25-minute CPU
+    run, so the digests are committed): BASELINE.json's fluid_million (1 000 000 particles) through
+    280 substeps, the same scene with vorticity for the 3 substeps before the reference blows up,
+    and the 16 M-particle block of the multi-GPU runs."""
     import json
     from fluidsimulator_b200.capi import Solver
     path = G.GOLDEN / "million.json"
-    if not path.exists():
-        pytest.skip("tests/golden/million.json not generated")
-    gold = json.loads(path.read_text())
-    params, planes, state = scenes.load_scene(scenes.SCENES["fluid_million"])
-    params = H.configure(params, H.STABLE_FLAGS)
+    gold = json.loads(path.read_text())["runs"] if path.exists() else {}
+    if run not in gold:
+        pytest.skip(f"tests/golden/million.json has no entry {run}")
+    gold = gold[run]
+    scene_name, flagname = run.split(":")
+    scene = scenes.block_16m() if scene_name == "block_16m" else scenes.SCENES[scene_name]
+    params, planes, state = scenes.load_scene(scene)
+    params = H.configure(params, FLAGSETS[flagname])
     assert len(state[0]) == gold["particles"]
     sol = Solver(0, len(state[0]))
     sol.set_params(params)
@@ -230,7 +236,8 @@ def test_fluid_million_matches_the_reference_digests(built):
         done = step
         got = {name: G.digest(a) for name, a in zip(G.STATE, sol.download())}
         bad = [name for name in G.STATE if got[name] != gold["steps"][str(step)][name]]
-        assert bad == [], f"substep {step}: {bad} differ from the reference"
+        assert bad == [], f"{run}, substep {step}: {bad} differ from the reference"
+    sol.close()
 
 
 def test_strict_follows_the_reference_through_its_blow_up(built):
