@@ -112,9 +112,12 @@ int ensure_particles(pbf_ctx* ctx, size_t n, size_t keep) {
   PBF_CUDA(ctx, ctx->pos_bak.grow_keep(cap, keep));
   PBF_CUDA(ctx, ctx->vel_bak.grow_keep(cap, keep));
   PBF_CUDA(ctx, ctx->pred_o.reserve(cap));
-  // + 2: the neighbour kernel may load (and ignore) the slot after the last particle
+  // + 2: the neighbour kernel may load (and ignore) the slot after the last particle, which is
+  // padding or a slot no substep has written yet — zero-filled once so that the load is defined
   PBF_CUDA(ctx, ctx->pred_a.reserve(tot + 2));
   PBF_CUDA(ctx, ctx->pred_b.reserve(tot + 2));
+  PBF_CUDA(ctx, cudaMemsetAsync(ctx->pred_a.p, 0, ctx->pred_a.n * sizeof(float4), ctx->stream));
+  PBF_CUDA(ctx, cudaMemsetAsync(ctx->pred_b.p, 0, ctx->pred_b.n * sizeof(float4), ctx->stream));
   PBF_CUDA(ctx, ctx->pos_s.reserve(tot));
   PBF_CUDA(ctx, ctx->vel_a.reserve(tot));
   PBF_CUDA(ctx, ctx->vel_b.reserve(tot));
