@@ -1,4 +1,5 @@
-"""Seconds-scale parity check on the GPU box without pytest/torch start-up: smoke() and a
+"""(Test infrastructure: compares with the oracle, like the tests it calls.)  Seconds-scale parity
+check on the GPU box without pytest/torch start-up: smoke() and a
 selection of the -m gpu tests called directly (oracle comparisons of grid, neighbour lists and
 state; table overflow and replay; random clouds; slabs).  The full suite is `pytest tests -m gpu`."""
 import sys
@@ -7,7 +8,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tests"))  # the test modules import helpers / golden_util by name
 
 t_all = time.perf_counter()
 
