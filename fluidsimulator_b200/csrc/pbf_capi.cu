@@ -513,8 +513,14 @@ int pbf_set_graph(pbf_ctx* ctx, int enabled) {
   return PBF_OK;
 }
 
-int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py, const float* pz, const float* vx,
-               const float* vy, const float* vz) {
+}  // extern "C"
+
+namespace {
+// wait: the host arrays may be reused on return (pbf_upload).  pbf_step_host keeps them alive for
+// the whole call and everything that follows is ordered on the same stream, so it does not wait
+// (one host round trip less per substep of the cuda_step contract).
+int upload_state(pbf_ctx* ctx, size_t n, const float* px, const float* py, const float* pz, const float* vx,
+                 const float* vy, const float* vz, bool wait) {
   if (!ctx) return PBF_E_INVALID;
   if (n > 0 && (!px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_upload: null array");
   if (n > 0x7fffffffu - 64) return fail(ctx, PBF_E_INVALID, "pbf_upload: more than 2^31 particles in one slab");
@@ -530,8 +536,16 @@ int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py, const f
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->soa[a].p, src[a], n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   const float* dsoa[6] = {ctx->soa[0].p, ctx->soa[1].p, ctx->soa[2].p, ctx->soa[3].p, ctx->soa[4].p, ctx->soa[5].p};
   ctx->launch_count += launch_pack_state(dsoa, ctx->pos_o.p, ctx->vel_o.p, (int)n, ctx->stream);
-  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host arrays may be reused on return
+  if (wait) PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PBF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py, const float* pz, const float* vx,
+               const float* vy, const float* vz) {
+  return upload_state(ctx, n, px, py, pz, vx, vy, vz, true);
 }
 
 int pbf_download(pbf_ctx* ctx, float* px, float* py, float* pz, float* vx, float* vy, float* vz) {
@@ -625,7 +639,7 @@ int pbf_host_unregister(pbf_ctx* ctx, void* ptr) {
 }
 
 int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz, int nsteps) {
-  int rc = pbf_upload(ctx, n, px, py, pz, vx, vy, vz);
+  int rc = upload_state(ctx, n, px, py, pz, vx, vy, vz, false);
   if (rc != PBF_OK) return rc;
   if ((rc = pbf_step(ctx, nsteps)) != PBF_OK) return rc;
   return pbf_download(ctx, px, py, pz, vx, vy, vz);
