@@ -58,6 +58,19 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(scene: str, presteps: int, stage: str, brick: bool):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the SAME regime
+    (profiles/ncu_traffic.json, keyed "<scene>:<t0|settled>:<kernel>", written by tools/ncu_traffic.py),
+    or None when there is no capture of that kernel in that regime."""
+    tf = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        table = json.loads(tf.read_text())
+    except Exception:
+        return None
+    regime = "t0" if presteps < 60 else "settled"
+    return table.get(f"{scene}:{regime}:{stage}{'_brick' if brick else ''}")
+
+
 def load_scene(name: str, flags: dict, iterations: int):
     from fluidsimulator_b200 import scenes
     if name in scenes.SCENES:
@@ -179,12 +192,100 @@ def run_reference(args, flags):
         "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.scene, "particles": n, "solver_iterations": args.iterations,
-                   "flags": args.flags, "dt": "1/120", "backend": "cpu"},
+                   "flags": args.flags, "dt": "1/120", "backend": "cpu", "presteps": 0,
+                   "note": "the CPU arm is timed from t0 (a substep costs it 1.6-2.5 s; pre-stepping to the settled "
+                           "regime would take minutes): its t0 substeps are its CHEAPEST, so the ratio is conservative"},
         "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def golden_digest(scene: str, flagname: str, iterations: int, mode: str):
+    """(substep, expected combined16) of the reference's own state digest for this workload
+    (tests/golden/million.json, written by tests/golden/make_golden_million.py from the unmodified
+    reference CPU solver), or None when no digest is committed for it."""
+    if iterations != 4 or mode != "strict":
+        return None
+    path = ROOT / "tests" / "golden" / "million.json"
+    try:
+        run = json.loads(path.read_text())["runs"][f"{scene}:{flagname}"]
+    except Exception:
+        return None
+    step = min(int(k) for k in run["steps"])
+    return step, run["steps"][str(step)]["combined16"]
+
+
+def combined16(state6) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for a in state6:
+        h.update(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+    return h.hexdigest()[:16]
+
+
+def parity_witness(sol, state, scene: str, flagname: str, iterations: int, mode: str, done: int = 0):
+    """Steps `sol` (at substep `done` of a run from t0) to the substep the committed reference digest
+    was taken at and compares.  Returns (witness dict or None, substeps now done)."""
+    gold = golden_digest(scene, flagname, iterations, mode)
+    if gold is None or gold[0] < done:
+        return None, done
+    step, expected = gold
+    sol.step(step - done)
+    got = combined16(sol.download())
+    return {"step": step, "combined16": got, "expected": expected, "ok": got == expected,
+            "source": "tests/golden/million.json (unmodified reference CPU solver)"}, step
+
+
+def timed_steps(sol, stream, steps: int) -> float:
+    """CUDA-event milliseconds of `steps` device-resident substeps on `stream`."""
+    import torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    sol.step(steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1)
+
+
+def extra_regimes(args, local: int, stream, mode) -> dict:
+    """SURVEY §8d's other regimes, device-timed the same way as `value` (extra keys, not the headline):
+    the free-fall lattice at t0, no flags, all flags for the 3 substeps before the reference blows
+    up, BASELINE.json's fluid_large iteration sweep, fluid_xlarge, and the 16 M block."""
+    from fluidsimulator_b200.capi import Solver
+    out = {}
+
+    def run(key, scene, flagname, iterations, presteps, warm, steps, restart=False):
+        try:
+            params, planes, state = load_scene(scene, FLAGSETS[flagname], iterations)
+            n = len(state[0])
+            sol = Solver(local, n, mode)
+            sol.set_params(params)
+            sol.set_planes(planes)
+            sol.set_stream(stream.cuda_stream)
+            sol.upload(state)
+            sol.step(presteps + warm)
+            if restart:  # graph captured and tables sized; the timed substeps start from t0 again
+                sol.upload(state)
+            ms = timed_steps(sol, stream, steps)
+            out[key] = {"value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps, "particles": n, "scene": scene,
+                        "flags": flagname, "solver_iterations": iterations,
+                        "substeps": [0 if restart else presteps + warm, (0 if restart else presteps + warm) + steps],
+                        "brick_path": sol.brick_status()["active"]}
+            sol.close()
+        except Exception as e:  # an extra must never take the headline down
+            out[key] = {"error": str(e)[:200]}
+
+    k, w = args.steps, args.warmup
+    run("value_t0", args.scene, args.flags, args.iterations, 0, w, k)
+    run("value_noflags", args.scene, "none", args.iterations, 0, w, k)
+    run("value_allflags_3steps", args.scene, "all", args.iterations, 0, 3, 3, restart=True)
+    for it in (2, 4, 8):
+        run(f"fluid_large_iters{it}", "fluid_large", "all", it, 0, 3, 3, restart=True)
+    run("fluid_xlarge", "fluid_xlarge", args.flags, args.iterations, 0, w, k)
+    run("block_16m", "block_16m", args.flags, args.iterations, 0, 3, min(k, 10))
+    return out
 
 
 def run_ours(args, flags):
@@ -211,41 +312,39 @@ def run_ours(args, flags):
     sol.set_planes(planes)
     sol.set_stream(stream.cuda_stream)
     sol.upload(state)
+    # With vorticity on the REFERENCE trajectory blows up after a few substeps: every
+    # phase then restarts from t0 so that no phase runs deeper into the blow-up than the timed one.
+    restart = bool(flags["vort"])
+    presteps = 0 if restart else args.presteps
 
     with torch.cuda.stream(stream):
-        if args.presteps:
-            sol.step(args.presteps)
+        # parity witness inside the driver-run line: the state this very context reaches must hash to
+        # what the unmodified reference CPU solver produced (then the run continues to the timed regime)
+        parity, done = parity_witness(sol, state, args.scene, args.flags, args.iterations, args.mode)
+        if restart and done:
+            sol.upload(state)
+            done = 0
+        if presteps > done:
+            sol.step(presteps - done)
         sol.step(args.warmup)
         torch.cuda.synchronize()
         sampler = ClockSampler(local)
         launches0 = sol.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler.start()
-        ev0.record(stream)
-        sol.step(args.steps)          # K substeps, device resident, one graph replay per substep
-        ev1.record(stream)
-        torch.cuda.synchronize()
+        ms = timed_steps(sol, stream, args.steps)   # K substeps, device resident, one graph replay per substep
         clocks = sampler.stop()
-        ms = ev0.elapsed_time(ev1)
         launches = sol.launch_count() - launches0
         nbr_total = sol.debug_sizes()[1]
+        brick = sol.brick_status()
 
-        # With vorticity on the REFERENCE trajectory blows up after a few substeps: every
-        # phase then restarts from t0 so that no phase runs deeper into the blow-up than the timed one.
-        restart = bool(flags["vort"])
         if restart:
             sol.upload(state)
             sol.step(args.warmup)
         # per-stage CUDA-event timing of the same K substeps' successors (profiling disables the graph)
         sol.profile_enable(True)
         sol.profile_reset()
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record(stream)
-        sol.step(args.steps)
-        pe1.record(stream)
-        torch.cuda.synchronize()
+        ms_prof = timed_steps(sol, stream, args.steps)
         prof = sol.profile()
-        ms_prof = pe0.elapsed_time(pe1)
         sol.profile_enable(False)
 
         # e2e: the reference-facing call (cuda_step contract): pinned host arrays in and out every step
@@ -262,13 +361,14 @@ def run_ours(args, flags):
             sol.step_host(host, 1)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        sol.close()
+        extras = {} if args.no_extras else extra_regimes(args, local, stream, mode)
 
     value = n * args.steps / (ms * 1e-3)
     peak, peak_src = measured_peaks()
     stages = {}
     for name, rec in prof.items():
         if rec["launches"] and rec["ms"] > 0:
-            per_launch_ms = rec["ms"] / rec["launches"] * (3 if name == "sort" else 1)
             stages[name] = {"ms_per_step": rec["ms"] / args.steps, "launches_per_step": rec["launches"] / args.steps}
     solver = {k: v for k, v in stages.items() if k in ("lambda", "delta")}
     dom = max(solver, key=lambda k: solver[k]["ms_per_step"]) if solver else None
@@ -276,15 +376,9 @@ def run_ours(args, flags):
     if dom:
         per_launch_s = 1e-3 * prof[dom]["ms"] / prof[dom]["launches"]
         achieved = ALG_BYTES[dom] * n / per_launch_s / 1e9
-        traffic = None
-        tf = ROOT / "profiles" / "ncu_traffic.json"
-        if tf.exists():
-            try:
-                traffic = json.loads(tf.read_text()).get(f"{args.scene}:{dom}")
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        roofline = {"bound": "hbm", "kernel": f"k_{dom}{'_brick' if brick['active'] else ''}", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(args.scene, presteps, dom, brick["active"]), "peak_source": peak_src,
                     "alg_bytes_per_particle": ALG_BYTES[dom], "avg_launch_ms": per_launch_s * 1e3,
                     "whole_step_frac": b_alg(args.iterations, flags) * value / 1e9 / peak}
 
@@ -294,19 +388,25 @@ def run_ours(args, flags):
         cpu_baseline = {"value": n * len(per) / float(sum(per)), "unit": "particle-substeps/s", "cores": threads,
                         "kind": kind, "sample": f"{args.scene} from t0, 1 warm-up + {len(per)} timed substeps, all host threads"}
 
+    entry_bytes = 2 if brick["active"] else 4
     line = {
         "metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.scene, "particles": n, "solver_iterations": args.iterations, "flags": args.flags,
-                   "mode": args.mode, "dt": "1/120", "presteps": args.presteps,
-                   "l2": f"working set exceeds L2: neighbour list {4 * nbr_total / 1e6:.0f} MB + {n * 16 * 9 / 1e6:.0f} MB of "
+                   "mode": args.mode, "dt": "1/120", "presteps": presteps,
+                   "timed_substeps": [presteps + args.warmup, presteps + args.warmup + args.steps],
+                   "kernels": "brick (shared-memory staged, 16-bit lists)" if brick["active"] else "global gather (32-bit lists)",
+                   "brick": brick,
+                   "l2": f"working set exceeds L2: neighbour list {entry_bytes * nbr_total / 1e6:.0f} MB + {n * 16 * 9 / 1e6:.0f} MB of "
                          "per-particle arrays are re-streamed every substep (no explicit flush)",
                    "avg_neighbors": nbr_total / n},
+        "parity": parity,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": n * e2e_steps / e2e_s, "unit": "particle-substeps/s", "h2d_bytes_per_step": 24 * n,
                 "d2h_bytes_per_step": 24 * n, "steps": e2e_steps, "call": "pbf_step_host (cuda_step contract)"},
         "gpu_launches": launches, "clocks": clocks, "stages": stages, "ms_per_step_profiled": ms_prof / args.steps,
+        "extra": extras,
     }
     print(json.dumps(line), flush=True)
 
@@ -320,7 +420,10 @@ def main():
     ap.add_argument("--scene", default=None)
     ap.add_argument("--flags", default="stable", choices=list(FLAGSETS))
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
-    ap.add_argument("--presteps", type=int, default=0)
+    ap.add_argument("--presteps", type=int, default=100,
+                    help="untimed substeps before the warm-up: 100 puts the timed region after the floor impact of "
+                         "fluid_million (substep ~82), SURVEY §8d; `extra.value_t0` is the free-fall lattice")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra regimes (extra.*)")
     ap.add_argument("--iterations", type=int, default=4)
     ap.add_argument("--weak", action="store_true", help="multi-GPU: 2M particles per GPU instead of one fixed scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -135,6 +135,8 @@ ABI = {
     "pbf_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pbf_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_set_brick": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_brick_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "pbf_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
     "pbf_download": (C.c_int, [C.c_void_p] + [_f32p] * 6),
     "pbf_step": (C.c_int, [C.c_void_p, C.c_int]),
@@ -252,6 +254,17 @@ class Solver:
 
     def set_graph(self, enabled: bool):
         self._check(self.lib.pbf_set_graph(self.ctx, int(enabled)))
+
+    def set_brick(self, enabled: bool):
+        """Brick kernels (shared-memory staged neighbourhoods, default) or the global-gather family."""
+        self._check(self.lib.pbf_set_brick(self.ctx, int(enabled)))
+
+    def brick_status(self) -> dict:
+        """Whether the last batch ran on the brick path, batches replayed without it, largest tile."""
+        fb, mt = C.c_uint64(), C.c_uint32()
+        rc = self.lib.pbf_brick_status(self.ctx, C.byref(fb), C.byref(mt))
+        self._check(min(rc, 0))
+        return {"active": rc == 1, "fallbacks": fb.value, "max_tile": mt.value}
 
     # -- state ---------------------------------------------------------------
     def upload(self, state6):

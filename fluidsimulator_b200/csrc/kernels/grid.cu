@@ -20,6 +20,7 @@
 //   * nothing here synchronises with the host: bounds, cell counts, the dense/sparse decision
 //     and overflow flags live in device memory (GridDesc / StatusBlock).
 #include "pbf_kernels.h"
+#include "neighbor_test.cuh"
 
 namespace pbf {
 
@@ -122,7 +123,8 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
 // on, SURVEY §0 — the substep switches to a SPARSE table: the same arrays, indexed by a hash of
 // the packed cell coordinates (`allow_sparse`; not in slab mode, whose ghost layers rely on the
 // x-major order of the dense key).
-__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad, NRef nr, int allow_sparse) {
+__global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad, NRef nr, int allow_sparse,
+                                int brick_cap) {
   pdl_wait();
   if (batch_failed(st)) return;
   unsigned long long cells = 1;
@@ -163,6 +165,26 @@ __global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_c
   desc->sparse = sparse ? 1 : 0;
   desc->overflow = overflow;
   if (overflow) st->grid_overflow = 1;
+  // brick path (brick.cu): bricks tile the dense table; a sparse table has no z-runs to stage
+  desc->nbricks = 0;
+  if (brick_cap > 0 && !overflow) {
+    if (!dense) {
+      st->brick_overflow |= kBrickDisable;
+    } else {
+      const unsigned long long bx = (unsigned)(desc->dim[0] + kBrickX - 1) / kBrickX, by = (unsigned)(desc->dim[1] + kBrickY - 1) / kBrickY,
+                               bz = (unsigned)(desc->dim[2] + kBrickZ - 1) / kBrickZ;
+      const unsigned long long nb = bx * by * bz;
+      if (nb > st->max_bricks) st->max_bricks = nb > 0xffffffffull ? 0xffffffffu : (unsigned int)nb;
+      if (nb > (unsigned long long)brick_cap) {
+        st->brick_overflow |= kBrickGrow;
+      } else {
+        desc->nbricks = (int)nb;
+        desc->bdim[0] = (int)bx;
+        desc->bdim[1] = (int)by;
+        desc->bdim[2] = (int)bz;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------- a4 cell keys
@@ -439,20 +461,9 @@ __device__ __forceinline__ void neighbors_cell(const float4* __restrict__ pred_s
 }
 #endif
 
-// PBF_NBR_MASK=1 (default): the candidate test and the list store are separated.  In the loop above
-// some lane of the warp has a hit in almost every step, so the whole warp walks through both store
-// blocks (62 instructions per candidate pair, 40 of them bookkeeping and control flow; SASS of
-// r01e).  Here the test loop only collects a bit per candidate (<= 32 candidates per chunk of a
-// cell: 25 instructions per pair) and has no hit-dependent control flow; the hits are then emitted
-// from the mask in ascending slot order (17 instructions per hit) — the order of the loop above.
-// The second candidate of a step is loaded unconditionally: the slot after the last particle is
-// padding (ensure_particles) and its bit is masked.
-// MEASURED on B200 (fluid_million, settled, profiles/ab_r01g_*.txt): 254 -> 228 us, bit-identical
-// state and lists; unrolling the test loop 2x / 4x (48 / 56 registers) gives the gain back.
-constexpr int kNbrMaskUnroll = PBF_NBR_MASK_UNROLL;  // candidate PAIRS per unrolled step of the test loop
-
-// List cursor of the mask variant: a pointer to the next entry instead of an element offset (two
-// instructions per hit for the address instead of four).
+// The test loop lives in neighbor_test.cuh (shared with the brick kernel).  List cursor of the mask
+// variant: a pointer to the next entry instead of an element offset (two instructions per hit for
+// the address instead of four).
 struct NbrCursor {
   uint32_t* p;    // entry `cnt` of this lane's list
   uint32_t cnt;
@@ -464,42 +475,6 @@ struct NbrCursor {
     cnt += 1u;
   }
 };
-
-template <bool CENTER>
-__device__ __forceinline__ void neighbors_cell_mask(const float4* __restrict__ pred_s, int2 range, float pz, f2 pxy,
-                                                    int i, float h2, NbrCursor& e) {
-#pragma unroll 1
-  for (int base = range.x; base < range.y; base += 32) {
-    const int end = min(range.y, base + 32);
-    uint32_t m = 0;
-#pragma unroll kNbrMaskUnroll
-    for (int j = base; j < end; j += 2) {
-      const float4 a0 = pred_s[j];
-      const float4 a1 = pred_s[j + 1];
-      const f2 d0 = __fadd2_rn(pxy, make_float2(-a0.x, -a0.y));
-      const f2 d1 = __fadd2_rn(pxy, make_float2(-a1.x, -a1.y));
-      const float z0 = __fsub_rn(pz, a0.z), z1 = __fsub_rn(pz, a1.z);
-      const f2 q0 = __fmul2_rn(d0, d0), q1 = __fmul2_rn(d1, d1);
-      const float r2a = __fadd_rn(__fadd_rn(q0.x, q0.y), __fmul_rn(z0, z0));
-      const float r2b = __fadd_rn(__fadd_rn(q1.x, q1.y), __fmul_rn(z1, z1));
-      // hits are shifted in from the top, two per step (core.cpp:231-240: strict r2 < h2)
-      m = (m >> 2) | ((r2a < h2) ? 0x40000000u : 0u) | ((r2b < h2) ? 0x80000000u : 0u);
-    }
-    const int lim = 32 - (end - base);            // 0 .. 31
-    m >>= lim & ~1;                               // candidate base + t at bit t (an odd chunk ran one slot over)
-    m &= 0xffffffffu >> lim;                      // ... whose bit is dropped here
-    if (CENTER) {
-      const uint32_t self = (uint32_t)(i - base);
-      if (self < 32u) m &= ~(1u << self);
-    }
-#pragma unroll 1
-    while (m) {
-      const int t = __ffs((int)m) - 1;
-      m &= m - 1u;
-      e.put(base + t);
-    }
-  }
-}
 
 // (an explicit minimum of 1 block per SM is not the same as none: ptxas then takes 52 registers
 // instead of 40)
@@ -629,12 +604,12 @@ int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConst
   if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
   PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1, g.desc, g.cell_key);
   if (slab) return 1;  // migrants extend the bounds; the table descriptor follows (launch_grid_finalize)
-  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1, n, 1);
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1, n, 1, g.bricks ? g.brick_cap : 0);
   return 2;
 }
 
 int launch_grid_finalize(const GridBuffers& g, int pad, NRef n, cudaStream_t s) {
-  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, pad, n, 0);
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, pad, n, 0, 0);
   return 1;
 }
 

@@ -40,12 +40,20 @@ struct GridBuffers {
   uint32_t* slot_id;    // n entries: particle id per slot before the cells are ordered by id
   unsigned long long* cell_key;  // cell_cap entries: packed coordinates per hash slot (sparse table), else empty
   uint32_t cell_cap;
+  BrickRec* bricks;     // brick path: brick_cap records, rewritten every substep (nullptr = brick path off)
+  int brick_cap;
 };
 
 struct NeighborList {
   uint32_t* idx;     // [(ceil(n/32)) * K * 32], pair-interleaved (see pbf_device.cuh); K even
   uint32_t* count;   // [n]
   int K;
+  // Brick path (brick.cu): `idx` then holds 16-bit tile-relative entries, entry k of slot i at
+  // ((uint16_t*)idx)[(i/32)*K*32 + (k/4)*128 + (i%32)*4 + k%4], and every pass that walks the list
+  // runs as one CTA per brick.  nullptr = global-gather family (32-bit entries).
+  const BrickRec* bricks = nullptr;
+  const GridDesc* desc = nullptr;
+  int brick_cap = 0;
 };
 
 // SoA host staging <-> float4 persistent state
@@ -91,6 +99,23 @@ typedef void (*StageCallback)(void* user, int stage_id, int begin);
 int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c,
                  int iterations, NRef n, bool strict, cudaStream_t s,
                  StageCallback cb, void* cb_user);
+// ---- brick path (kernels/brick.cu): the same stages as one CTA per brick of grid cells, halo staged
+// into shared memory with cp.async.bulk, 16-bit tile-relative neighbour entries ------------------
+int brick_setup();  // opt the kernels in to their dynamic shared memory (once per process / device)
+int launch_brick_table(const GridBuffers& g, cudaStream_t s);
+int launch_neighbors_brick(const float4* pred_s, const StepConsts& c, const GridBuffers& g, const NeighborList& nl,
+                           cudaStream_t s);
+int launch_lambda_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool strict,
+                        cudaStream_t s);
+int launch_delta_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
+                       bool is_final, bool strict, cudaStream_t s);
+int launch_xsph_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,
+                      bool strict, cudaStream_t s);
+int launch_vort_omega_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
+                            bool strict, cudaStream_t s);
+int launch_vort_apply_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
+                            bool strict, cudaStream_t s);
+
 // The individual passes (the slab driver puts halo exchanges between them).  `cur` selects the
 // pred ping-pong buffer a pass reads; delta writes pred[cur ^ 1].
 int launch_lambda(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, NRef n,

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -161,6 +162,17 @@ int ensure_tables(pbf_ctx* ctx) {
     // rows are only filled up to each particle's count; the debug surface copies whole rows
     PBF_CUDA(ctx, cudaMemsetAsync(ctx->nbr_idx.p, 0, need * sizeof(uint32_t), ctx->stream));
   }
+  if (ctx->brick_on) {
+    if (ctx->brick_cap < 1024) ctx->brick_cap = 1024;
+    // a first guess from the particle count: ~6 particles per cell at rest density, bounding box
+    // of a splash several times the fluid volume; the table grows on demand (kBrickGrow)
+    const size_t guess = slots / (size_t)(pbf::kBrickX * pbf::kBrickY * pbf::kBrickZ) + 1024;
+    if ((size_t)ctx->brick_cap < guess) ctx->brick_cap = (int)guess;
+    if (ctx->bricks.n < (size_t)ctx->brick_cap) {
+      invalidate_graph(ctx);
+      PBF_CUDA(ctx, ctx->bricks.reserve((size_t)ctx->brick_cap));
+    }
+  }
   if (ctx->debug) {
     PBF_CUDA(ctx, ctx->dbg_lambda.reserve(slots));
     PBF_CUDA(ctx, ctx->dbg_rho.reserve(slots));
@@ -226,6 +238,17 @@ void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g) {
   g.slot_id = ctx->slot_id.p;
   g.cell_key = ctx->cell_key.p;
   g.cell_cap = ctx->cell_cap;
+  g.bricks = ctx->brick_on ? ctx->bricks.p : nullptr;
+  g.brick_cap = ctx->brick_on ? ctx->brick_cap : 0;
+}
+
+void fill_neighbor_list(pbf_ctx* ctx, NeighborList& nl) {
+  nl.idx = ctx->nbr_idx.p;
+  nl.count = ctx->nbr_count.p;
+  nl.K = ctx->K;
+  nl.bricks = ctx->brick_on ? ctx->bricks.p : nullptr;
+  nl.desc = ctx->desc.p;
+  nl.brick_cap = ctx->brick_on ? ctx->brick_cap : 0;
 }
 
 void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
@@ -255,7 +278,8 @@ int enqueue_substep(pbf_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   GridBuffers g{};
   fill_grid_buffers(ctx, g);
-  NeighborList nl{ctx->nbr_idx.p, ctx->nbr_count.p, ctx->K};
+  NeighborList nl;
+  fill_neighbor_list(ctx, nl);
   const StepConsts& c = ctx->consts;
   StageTimer& t = ctx->timer;
   int launches = 0, k;
@@ -277,8 +301,14 @@ int enqueue_substep(pbf_ctx* ctx) {
   stage_mark(ctx, PBF_STAGE_CELLS, 0);
   t.launches[PBF_STAGE_CELLS] += k; launches += k;
 
+  if (nl.bricks) {  // brick path: runs of every brick (cells stage), then the list from shared-memory tiles
+    stage_mark(ctx, PBF_STAGE_CELLS, 1);
+    k = launch_brick_table(g, s);
+    stage_mark(ctx, PBF_STAGE_CELLS, 0);
+    t.launches[PBF_STAGE_CELLS] += k; launches += k;
+  }
   stage_mark(ctx, PBF_STAGE_NEIGHBORS, 1);
-  k = launch_neighbors(ctx->pred_a.p, c, g, nl, n, s);
+  k = nl.bricks ? launch_neighbors_brick(ctx->pred_a.p, c, g, nl, s) : launch_neighbors(ctx->pred_a.p, c, g, nl, n, s);
   stage_mark(ctx, PBF_STAGE_NEIGHBORS, 0);
   t.launches[PBF_STAGE_NEIGHBORS] += k; launches += k;
 
@@ -428,6 +458,12 @@ pbf_ctx* pbf_create(int device, size_t capacity) {
     return nullptr;
   }
   ctx->stream = ctx->own_stream;
+  if (const char* env = std::getenv("PBF_BRICK")) ctx->brick_want = env[0] != '0';
+  if (const int brc = brick_setup()) {
+    g_error = std::string("pbf_create: shared-memory opt-in of the brick kernels failed: ") + cudaGetErrorString((cudaError_t)brc);
+    pbf_destroy(ctx);
+    return nullptr;
+  }
   if (capacity > 0 && ensure_particles(ctx, capacity, 0) != PBF_OK) {
     g_error = ctx->error;
     pbf_destroy(ctx);
@@ -448,6 +484,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->keys0.release(); ctx->keys1.release(); ctx->vals0.release(); ctx->vals1.release();
   ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release(); ctx->cell_key.release();
   ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
+  ctx->bricks.release();
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
   ctx->dbg_dv.release(); ctx->dbg_eta.release();
@@ -577,7 +614,17 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
   // batch backup: a substep that overflows a device table is re-run after growing it
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_bak.p, ctx->pos_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  // brick path or global-gather family for this batch (a failed brick batch is replayed without it)
+  bool brick = ctx->brick_want && ctx->params.solver_iterations > 0;
+  if (brick && ctx->brick_retry > 0) {
+    ctx->brick_retry--;
+    brick = false;
+  }
   for (int attempt = 0; attempt < 32; ++attempt) {
+    if (brick != ctx->brick_on) {
+      ctx->brick_on = brick;
+      invalidate_graph(ctx);
+    }
     int rc = ensure_tables(ctx);
     if (rc != PBF_OK) return rc;
     if ((rc = reset_status(ctx)) != PBF_OK) return rc;
@@ -588,8 +635,9 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
     if (ctx->profile) timer_resolve(ctx);
     const StatusBlock st = *ctx->status_host;
     ctx->last_status = st;
-    if (!st.grid_overflow && !st.nbr_overflow) {
+    if (!st.grid_overflow && !st.nbr_overflow && !st.brick_overflow) {
       for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;  // core.cpp:614
+      ctx->last_brick = ctx->brick_on;
       return PBF_OK;
     }
     // grow and replay the batch from the backup: results never depend on table sizes
@@ -610,6 +658,16 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
       uint32_t cap = ctx->cell_cap;
       while ((unsigned long long)cap < max_cells + max_cells / 4) cap <<= 1;
       ctx->cell_cap = cap;
+      invalidate_graph(ctx);
+    }
+    if (st.brick_overflow & kBrickDisable) {
+      // a tile larger than kTileCap records, or the sparse cell table: this batch runs on the
+      // global-gather family; the brick path is tried again a few batches later
+      brick = false;
+      ctx->brick_retry = 16;
+      ctx->brick_fallbacks++;
+    } else if (st.brick_overflow & kBrickGrow) {
+      ctx->brick_cap = (int)std::min<unsigned long long>((unsigned long long)st.max_bricks + st.max_bricks / 4 + 64, 1ull << 28);
       invalidate_graph(ctx);
     }
     if (st.nbr_overflow) {
@@ -759,9 +817,38 @@ int pbf_debug_neighbors(pbf_ctx* ctx, int32_t* prefix_sum, int32_t* indices) {
   if ((rc = fetch(ctx, counts, ctx->nbr_count.p, n)) != PBF_OK) return rc;
 
   const size_t K = (size_t)ctx->K;
-  if ((rc = fetch(ctx, list, ctx->nbr_idx.p, ((n + 31) / 32) * K * 32)) != PBF_OK) return rc;
   std::vector<uint32_t> slot_of(n);
   for (size_t s = 0; s < n; ++s) slot_of[vals[s]] = (uint32_t)s;
+  if (ctx->last_brick) {
+    // brick path: 16-bit entries are byte offsets into the tile of the particle's brick; translate
+    // them back to sorted slots with the brick table of the last substep
+    const GridDesc d = ctx->last_desc;
+    std::vector<uint32_t> keys;
+    std::vector<BrickRec> recs;
+    std::vector<uint16_t> list16;
+    if ((rc = fetch(ctx, keys, ctx->sorted_buf ? ctx->keys1.p : ctx->keys0.p, n)) != PBF_OK) return rc;
+    if ((rc = fetch(ctx, recs, ctx->bricks.p, (size_t)d.nbricks)) != PBF_OK) return rc;
+    if ((rc = fetch(ctx, list16, reinterpret_cast<const uint16_t*>(ctx->nbr_idx.p), ((n + 31) / 32) * K * 32)) != PBF_OK) return rc;
+    const uint32_t dy = (uint32_t)d.dim[1], dz = (uint32_t)d.dim[2];
+    size_t total = 0;
+    for (size_t o = 0; o < n; ++o) {  // original particle order, like core.cpp:205
+      const size_t s = slot_of[o];
+      const uint32_t z = keys[s] % dz, y = (keys[s] / dz) % dy, x = keys[s] / (dz * dy);
+      const size_t b = ((size_t)(x / kBrickX) * (size_t)d.bdim[1] + (size_t)(y / kBrickY)) * (size_t)d.bdim[2] + (size_t)(z / kBrickZ);
+      const BrickRec& rec = recs[b];
+      const uint16_t* row = list16.data() + (s >> 5) * K * 32 + (s & 31) * 4;
+      for (uint32_t k = 0; k < counts[s]; ++k) {
+        const int te = (int)(row[(size_t)(k >> 2) * 128 + (k & 3)] >> 4);
+        int c = 0;
+        while (c + 1 < kBrickCols && rec.col_base[c + 1] <= te) ++c;
+        if (indices) indices[total] = (int32_t)vals[(size_t)(rec.col_start[c] + (te - rec.col_base[c]))];
+        ++total;
+      }
+      if (prefix_sum) prefix_sum[o] = (int32_t)total;
+    }
+    return PBF_OK;
+  }
+  if ((rc = fetch(ctx, list, ctx->nbr_idx.p, ((n + 31) / 32) * K * 32)) != PBF_OK) return rc;
   size_t total = 0;
   for (size_t o = 0; o < n; ++o) {  // original particle order, like core.cpp:205
     const size_t s = slot_of[o];
@@ -847,6 +934,23 @@ int pbf_debug_set_capacity(pbf_ctx* ctx, int K, uint32_t cell_cap) {
   ctx->cell_cap = cap;
   invalidate_graph(ctx);
   return PBF_OK;
+}
+
+// 1 = one CTA per brick of grid cells with shared-memory staged neighbourhoods (default, unless the
+// environment says PBF_BRICK=0), 0 = the global-gather kernels.  Same results bit for bit.
+int pbf_set_brick(pbf_ctx* ctx, int enabled) {
+  if (!ctx) return PBF_E_INVALID;
+  ctx->brick_want = enabled != 0;
+  ctx->brick_retry = 0;
+  return PBF_OK;
+}
+// 1 if the last completed pbf_step batch ran on the brick path; *fallbacks (may be NULL) counts the
+// batches that had to be replayed on the global-gather kernels, *max_tile the largest tile seen.
+int pbf_brick_status(const pbf_ctx* ctx, uint64_t* fallbacks, uint32_t* max_tile) {
+  if (!ctx) return PBF_E_INVALID;
+  if (fallbacks) *fallbacks = ctx->brick_fallbacks;
+  if (max_tile) *max_tile = ctx->last_status.max_tile;
+  return ctx->last_brick ? 1 : 0;
 }
 
 // Test hook (not in pbf_b200.h): 1 if the last substep used the sparse (hashed) cell table.

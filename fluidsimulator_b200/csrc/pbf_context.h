@@ -154,6 +154,17 @@ struct pbf_ctx {
   // neighbour list
   pbf::DevBuf<uint32_t> nbr_idx, nbr_count;
   int K = 96;
+  // brick path (kernels/brick.cu): one CTA per brick of grid cells, neighbourhood staged in shared
+  // memory, 16-bit tile-relative neighbour entries.  `brick_want` is the user's / environment's
+  // choice (PBF_BRICK=0 disables it), `brick_on` what the current batch attempt uses: a batch whose
+  // tiles do not fit (or that needs the sparse cell table) is replayed with the global-gather family
+  // and the brick path is tried again `brick_retry` batches later.
+  pbf::DevBuf<pbf::BrickRec> bricks;
+  int brick_cap = 0;
+  bool brick_want = true, brick_on = false;
+  int brick_retry = 0;
+  uint64_t brick_fallbacks = 0;
+  bool last_brick = false;        // the last completed batch ran on the brick path (debug surface)
   // SoA staging for upload / download
   pbf::DevBuf<float> soa[6];
   // debug scratch (sorted order)
@@ -193,6 +204,7 @@ int reset_status(pbf_ctx* ctx);
 void stage_mark(void* user, int stage, int begin);
 void timer_resolve(pbf_ctx* ctx);
 void fill_grid_buffers(pbf_ctx* ctx, GridBuffers& g);
+void fill_neighbor_list(pbf_ctx* ctx, NeighborList& nl);
 void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b);
 // pbf_slab.cu
 int slab_step(pbf_ctx* ctx, int nsteps);

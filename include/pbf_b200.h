@@ -104,6 +104,16 @@ int pbf_set_mode(pbf_ctx* ctx, int mode);
 int pbf_set_stream(pbf_ctx* ctx, void* cuda_stream);
 /* 1 = replay each substep as a CUDA graph (default), 0 = plain stream launches. */
 int pbf_set_graph(pbf_ctx* ctx, int enabled);
+/* Kernel family of the neighbour build and the solver passes.  1 (default; environment PBF_BRICK=0
+ * changes it) = one CTA per brick of grid cells, the brick's neighbourhood staged into shared memory
+ * by TMA bulk copies, 16-bit tile-relative neighbour lists.  0 = one thread per particle gathering
+ * from global memory (what replaces reference cuda_stub.cu:155-416 either way).  Results are
+ * bit-identical; a batch the brick path cannot hold (tile capacity, sparse cell table of a diverged
+ * scene) is transparently replayed on the other family. */
+int pbf_set_brick(pbf_ctx* ctx, int enabled);
+/* Returns 1 if the last pbf_step batch ran on the brick path, 0 if not; optional outputs: batches
+ * replayed on the global-gather family so far, largest tile (records) of the last batch. */
+int pbf_brick_status(const pbf_ctx* ctx, uint64_t* fallbacks, uint32_t* max_tile);
 
 /* Host SoA -> device (the six H2D copies of reference cuda_stub.cu:791-796).
  * Resets nothing else; time is kept (use pbf_set_time). */

@@ -31,7 +31,10 @@ def setup(scene, vort):
 
 
 sol = setup("fluid_large", 1)
-sol.step(40)
+sol.step(3)
+print("large_all_3 brick", sol.brick_status(), flush=True)
+sol.step(37)
+print("large_all_40 brick", sol.brick_status(), flush=True)
 d = digest(sol.download())
 print(f"large_all_40 {d} {'IDENTICAL' if d == EXPECT_LARGE_ALL_40 else 'DIFFERS'} ({time.perf_counter() - t00:.1f} s)", flush=True)
 sol.close()
@@ -49,5 +52,6 @@ sol.profile_reset()
 sol.step(20)
 prof = sol.profile()
 print("stage_us", {k: round(1e3 * v["ms"] / v["launches"], 1) for k, v in prof.items() if v["launches"]}, flush=True)
+print("million brick", sol.brick_status(), flush=True)
 d = digest(sol.download())
 print(f"million_280 {d} {'IDENTICAL' if d == EXPECT_MILLION_280 else 'DIFFERS'} ({time.perf_counter() - t00:.1f} s)", flush=True)
