@@ -415,23 +415,28 @@ k_neighbors_brick(const float4* __restrict__ pred_s, const int2* __restrict__ ce
   }
 }
 
-// ---------------------------------------------------------------- a8 lambda
+// ================================================================== the passes that walk the list
+// A pass is an Op: which arrays it stages (kTiles tiles with the same layout) and what it does for
+// one owned particle.  Two drivers run an Op:
+//   k_brick_once     one CTA per brick (brick v1): stage, wait, walk the owned particles kBT at a time;
+//   k_brick_persist  persistent CTAs (brick v2): a ring of kPS tile slots per CTA filled by cp.async.bulk
+//                    while the warps work on earlier slots; bricks are handed out through a global
+//                    ticket, the owned particles of a brick 32 at a time through a shared-memory
+//                    counter, so a warp never waits for the slowest warp of its CTA, the staging of
+//                    brick k+1.. overlaps the arithmetic of brick k, and there is no per-brick tail.
 template <bool S, bool SAFE>
-__global__ void __launch_bounds__(kBT, PBF_BRICK_MINBLOCKS)
-k_lambda_brick(float4* __restrict__ pred, const uint16_t* __restrict__ nbr, const uint32_t* __restrict__ nbr_count,
-               float* __restrict__ rho_out, const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc,
-               StepConsts c, const StatusBlock* st, DebugPtrs dbg, int K) {
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ BrickShared sh;
-  pdl_wait();
-  if (!brick_begin(sh, bricks, desc, st)) return;
-  brick_stage(sh, dyn, pred);
-  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.bar, (uint32_t)sh.rec.tile_n * 16u);
-  mbar_wait(&sh.bar, 0);
-  for_each_owned<kBT>(sh.rec, nbr, nbr_count, K, [&](const Owned& o, const uint2* row, uint32_t cnt, uint2 first) {
-    const float4 pi = lds128(dyn, o.off);
+struct LambdaOp {  // a8
+  static constexpr int kTiles = 1;
+  float4* pred;
+  float* rho_out;
+  StepConsts c;
+  DebugPtrs dbg;
+  __device__ __forceinline__ const float4* source(int) const { return pred; }
+  __device__ __forceinline__ void particle(const Owned& o, const uint2* row, uint32_t cnt, uint2 first,
+                                           const unsigned char* ta, const unsigned char*) const {
+    const float4 pi = lds128(ta, o.off);
     LambdaPass<S, SAFE> acc(pi, c);
-    tile_pairs(row, cnt, first, dyn, pi, acc);
+    tile_pairs(row, cnt, first, ta, pi, acc);
     float lambda, rho;
     acc.finish(lambda, rho);
     // only .w is written; the tiles other CTAs stage from pred use .xyz only in this pass
@@ -439,57 +444,57 @@ k_lambda_brick(float4* __restrict__ pred, const uint16_t* __restrict__ nbr, cons
     rho_out[o.i] = rho;
     if (dbg.lambda) dbg.lambda[o.i] = lambda;
     if (dbg.rho) dbg.rho[o.i] = rho;
-  });
-}
+  }
+};
 
-// ---------------------------------------------------------------- a9 + a10 (+ a11, a14)
 template <bool S, bool LAST, bool COMMON>
-__global__ void __launch_bounds__(kBT, PBF_BRICK_MINBLOCKS)
-k_delta_brick(const float4* __restrict__ pred_in, float4* __restrict__ pred_out, const uint16_t* __restrict__ nbr,
-              const uint32_t* __restrict__ nbr_count, const float4* __restrict__ pos_s, const float* __restrict__ rho,
-              float4* __restrict__ vel_out, const float4* __restrict__ planes, float4* __restrict__ pos_o,
-              float4* __restrict__ vel_o, const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc,
-              StepConsts c, const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final, int K) {
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ BrickShared sh;
-  pdl_wait();
-  if (!brick_begin(sh, bricks, desc, st)) return;
-  brick_stage(sh, dyn, pred_in);
-  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.bar, (uint32_t)sh.rec.tile_n * 16u);
-  mbar_wait(&sh.bar, 0);
-  for_each_owned<kBT>(sh.rec, nbr, nbr_count, K, [&](const Owned& o, const uint2* row, uint32_t cnt, uint2 first) {
-    const float4 pi = lds128(dyn, o.off);
+struct DeltaOp {  // a9 + a10 (+ a11, a14)
+  static constexpr int kTiles = 1;
+  const float4* pred_in;
+  float4* pred_out;
+  const float4* pos_s;
+  const float* rho;
+  float4* vel_out;
+  const float4* planes;
+  float4* pos_o;
+  float4* vel_o;
+  StepConsts c;
+  DebugPtrs dbg;
+  HaloOut halo;
+  int is_final;
+  __device__ __forceinline__ const float4* source(int) const { return pred_in; }
+  __device__ __forceinline__ void particle(const Owned& o, const uint2* row, uint32_t cnt, uint2 first,
+                                           const unsigned char* ta, const unsigned char*) const {
+    const float4 pi = lds128(ta, o.off);
     DeltaPass<S, COMMON> acc(pi, c);
-    tile_pairs(row, cnt, first, dyn, pi, acc);
+    tile_pairs(row, cnt, first, ta, pi, acc);
     V3<FT<S>> np;
     float4 dlt;
     acc.finish(pi, planes, np, dlt);
     // the brick family's XSPH stages positions and velocities as two tiles: no 32-byte records
     delta_store<S, LAST>(o.i, np, dlt, pred_out, pos_s, rho, vel_out, (PosVel*)nullptr, planes, pos_o, vel_o, c, dbg,
                          halo, is_final);
-  });
-}
+  }
+};
 
-// ---------------------------------------------------------------- a12 XSPH
 template <bool S>
-__global__ void __launch_bounds__(kBT2, PBF_BRICK_MINBLOCKS)
-k_xsph_brick(const float4* __restrict__ pos, const float4* __restrict__ vel_in, float4* __restrict__ vel_out,
-             const uint16_t* __restrict__ nbr, const uint32_t* __restrict__ nbr_count, const float4* __restrict__ pos_s,
-             const float4* __restrict__ planes, float4* __restrict__ pos_o, float4* __restrict__ vel_o,
-             const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc, StepConsts c,
-             const StatusBlock* st, DebugPtrs dbg, HaloOut halo, int is_final, int K) {
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ BrickShared sh;
-  using F = FT<S>;
-  pdl_wait();
-  if (!brick_begin(sh, bricks, desc, st)) return;
-  unsigned char* ta = dyn;
-  unsigned char* tb = dyn + kTileBytes;
-  brick_stage(sh, ta, pos);
-  brick_stage(sh, tb, vel_in);
-  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.bar, (uint32_t)sh.rec.tile_n * 32u);
-  mbar_wait(&sh.bar, 0);
-  for_each_owned<kBT2>(sh.rec, nbr, nbr_count, K, [&](const Owned& o, const uint2* row, uint32_t cnt, uint2 first) {
+struct XsphOp {  // a12
+  static constexpr int kTiles = 2;
+  const float4* pos;
+  const float4* vel_in;
+  float4* vel_out;
+  const float4* pos_s;
+  const float4* planes;
+  float4* pos_o;
+  float4* vel_o;
+  StepConsts c;
+  DebugPtrs dbg;
+  HaloOut halo;
+  int is_final;
+  __device__ __forceinline__ const float4* source(int k) const { return k ? vel_in : pos; }
+  __device__ __forceinline__ void particle(const Owned& o, const uint2* row, uint32_t cnt, uint2 first,
+                                           const unsigned char* ta, const unsigned char* tb) const {
+    using F = FT<S>;
     const float4 pi = lds128(ta, o.off), vi = lds128(tb, o.off);
     XsphPass<S> acc(pi, vi, c);
     tile_pairs2(row, cnt, first, ta, tb, pi, vi, acc);
@@ -502,27 +507,19 @@ k_xsph_brick(const float4* __restrict__ pos, const float4* __restrict__ vel_in, 
       vel_out[o.i] = vo;
       halo.put(o.i, vo);
     }
-  });
-}
+  }
+};
 
-// ---------------------------------------------------------------- a13 vorticity, pass 1
 template <bool S>
-__global__ void __launch_bounds__(kBT2, PBF_BRICK_MINBLOCKS)
-k_vort_omega_brick(float4* __restrict__ pos, const float4* __restrict__ vel, float4* __restrict__ omega,
-                   const uint16_t* __restrict__ nbr, const uint32_t* __restrict__ nbr_count,
-                   const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc, StepConsts c,
-                   const StatusBlock* st, int K) {
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ BrickShared sh;
-  pdl_wait();
-  if (!brick_begin(sh, bricks, desc, st)) return;
-  unsigned char* ta = dyn;
-  unsigned char* tb = dyn + kTileBytes;
-  brick_stage(sh, ta, pos);
-  brick_stage(sh, tb, vel);
-  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.bar, (uint32_t)sh.rec.tile_n * 32u);
-  mbar_wait(&sh.bar, 0);
-  for_each_owned<kBT2>(sh.rec, nbr, nbr_count, K, [&](const Owned& o, const uint2* row, uint32_t cnt, uint2 first) {
+struct OmegaOp {  // a13, pass 1
+  static constexpr int kTiles = 2;
+  float4* pos;
+  const float4* vel;
+  float4* omega;
+  StepConsts c;
+  __device__ __forceinline__ const float4* source(int k) const { return k ? vel : pos; }
+  __device__ __forceinline__ void particle(const Owned& o, const uint2* row, uint32_t cnt, uint2 first,
+                                           const unsigned char* ta, const unsigned char* tb) const {
     const float4 pi = lds128(ta, o.off), vi = lds128(tb, o.off);
     OmegaPass<S> acc(pi, vi, c);
     tile_pairs2(row, cnt, first, ta, tb, pi, vi, acc);
@@ -530,33 +527,212 @@ k_vort_omega_brick(float4* __restrict__ pos, const float4* __restrict__ vel, flo
     omega[o.i] = om;
     // |omega_i| rides in pos[i].w for the eta pass; the tiles staged from pos use .xyz only here
     reinterpret_cast<float*>(pos + o.i)[3] = om.w;
-  });
-}
+  }
+};
 
-// ---------------------------------------------------------------- a13 pass 2 + apply (+ a14)
 template <bool S>
-__global__ void __launch_bounds__(kBT, PBF_BRICK_MINBLOCKS)
-k_vort_apply_brick(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ omega,
-                   const uint16_t* __restrict__ nbr, const uint32_t* __restrict__ nbr_count,
-                   const float4* __restrict__ pos_s, const float4* __restrict__ planes, float4* __restrict__ pos_o,
-                   float4* __restrict__ vel_o, const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc,
-                   StepConsts c, const StatusBlock* st, DebugPtrs dbg, int K) {
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ BrickShared sh;
-  using F = FT<S>;
-  pdl_wait();
-  if (!brick_begin(sh, bricks, desc, st)) return;
-  brick_stage(sh, dyn, pos);
-  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.bar, (uint32_t)sh.rec.tile_n * 16u);
-  mbar_wait(&sh.bar, 0);
-  for_each_owned<kBT>(sh.rec, nbr, nbr_count, K, [&](const Owned& o, const uint2* row, uint32_t cnt, uint2 first) {
-    const float4 pi = lds128(dyn, o.off);  // (pos xyz, |omega_i|)
+struct EtaOp {  // a13 pass 2 + apply (+ a14)
+  static constexpr int kTiles = 1;
+  const float4* pos;
+  const float4* vel;
+  const float4* omega;
+  const float4* pos_s;
+  const float4* planes;
+  float4* pos_o;
+  float4* vel_o;
+  StepConsts c;
+  DebugPtrs dbg;
+  __device__ __forceinline__ const float4* source(int) const { return pos; }
+  __device__ __forceinline__ void particle(const Owned& o, const uint2* row, uint32_t cnt, uint2 first,
+                                           const unsigned char* ta, const unsigned char*) const {
+    using F = FT<S>;
+    const float4 pi = lds128(ta, o.off);  // (pos xyz, |omega_i|)
     EtaPass<S> acc(pi, c);
-    tile_pairs(row, cnt, first, dyn, pi, acc);
+    tile_pairs(row, cnt, first, ta, pi, acc);
     if (dbg.eta) dbg.eta[o.i] = make_float4(acc.ex, acc.ey, acc.ez, 0.0f);
     const V3<F> v = acc.finish(omega[o.i], vel[o.i]);
     finalize_particle<F>(pi, v, __float_as_uint(pos_s[o.i].w), c, planes, pos_o, vel_o);
+  }
+};
+
+// ---- driver 1: one CTA per brick --------------------------------------------------------------
+template <typename Op>
+__global__ void __launch_bounds__(kBT, PBF_BRICK_MINBLOCKS)
+k_brick_once(const __grid_constant__ Op op, const uint16_t* __restrict__ nbr, const uint32_t* __restrict__ nbr_count,
+             const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc, const StatusBlock* st, int K) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ BrickShared sh;
+  pdl_wait();
+  if (!brick_begin(sh, bricks, desc, st)) return;
+  unsigned char* ta = dyn;
+  unsigned char* tb = dyn + (Op::kTiles > 1 ? kTileBytes : 0);
+#pragma unroll
+  for (int k = 0; k < Op::kTiles; ++k) brick_stage(sh, dyn + (size_t)k * kTileBytes, op.source(k));
+  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.bar, (uint32_t)sh.rec.tile_n * 16u * Op::kTiles);
+  mbar_wait(&sh.bar, 0);
+  for_each_owned<kBT>(sh.rec, nbr, nbr_count, K, [&](const Owned& o, const uint2* row, uint32_t cnt, uint2 first) {
+    op.particle(o, row, cnt, first, ta, tb);
   });
+}
+
+// ---- driver 2: persistent CTAs, ring of tile slots ---------------------------------------------
+#ifndef PBF_PERSIST_THREADS
+#define PBF_PERSIST_THREADS 512   // one-tile passes: 2 CTAs per SM
+#endif
+#ifndef PBF_PERSIST_THREADS2
+#define PBF_PERSIST_THREADS2 768   // two-tile passes (XSPH, omega): 1 CTA per SM, up to 85 registers
+#endif
+#ifndef PBF_PERSIST_SLOTS
+#define PBF_PERSIST_SLOTS 3
+#endif
+constexpr int kPS = PBF_PERSIST_SLOTS;
+
+struct PSlot {
+  BrickRec rec;
+  unsigned long long full;  // mbarrier: record and tile(s) of the slot are in place (or the ring ran dry)
+  int brick;                // brick index, -1 = no more work
+  int next;                 // next owned particle of the brick to hand out
+  int left;                 // warps that are done with the slot
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One warp (all lanes) puts the next non-empty brick into slot `sl`: ticket, record, bulk copies.
+template <typename Op>
+__device__ __forceinline__ void persist_refill(const Op& op, PSlot& sl, unsigned char* tiles,
+                                               const BrickRec* __restrict__ bricks, int nbricks, unsigned int* ticket,
+                                               int lane) {
+  int b = -1;
+  if (lane == 0) {
+    for (;;) {
+      const unsigned int t = atomicAdd(ticket, 1u);
+      if (t >= (unsigned int)nbricks) break;
+      if (bricks[t].own_n > 0) { b = (int)t; break; }
+    }
+  }
+  b = __shfl_sync(0xffffffffu, b, 0);
+  if (b < 0) {
+    if (lane == 0) {
+      sl.brick = -1;
+      mbar_arrive(&sl.full);
+    }
+    return;
+  }
+  const int* src = reinterpret_cast<const int*>(bricks + b);
+  int* dst = reinterpret_cast<int*>(&sl.rec);
+  for (int w = lane; w < (int)(sizeof(BrickRec) / sizeof(int)); w += 32) dst[w] = src[w];
+  if (lane == 0) {
+    sl.brick = b;
+    sl.next = 0;
+    sl.left = 0;
+  }
+  __syncwarp();
+  // the slot's previous tile was read through the generic proxy; the bulk copies write through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (lane == 0) mbar_arrive_expect_tx(&sl.full, (uint32_t)sl.rec.tile_n * 16u * Op::kTiles);
+  for (int c = lane; c < kBrickCols; c += 32) {
+    const int base = sl.rec.col_base[c], len = sl.rec.col_base[c + 1] - base;
+    if (len > 0) {
+#pragma unroll
+      for (int k = 0; k < Op::kTiles; ++k)
+        bulk_g2s(tiles + (size_t)k * kTileBytes + (size_t)base * 16u, op.source(k) + sl.rec.col_start[c],
+                 (uint32_t)len * 16u, &sl.full);
+    }
+  }
+}
+
+// ctl[0] = brick ticket, ctl[1] = CTAs that have finished; the last CTA out resets both, so every
+// launch (they are stream-ordered) starts from zero without a memset in the graph.
+template <typename Op, int kPT, int MINB>
+__global__ void __launch_bounds__(kPT, MINB)
+k_brick_persist(const __grid_constant__ Op op, const uint16_t* __restrict__ nbr, const uint32_t* __restrict__ nbr_count,
+                const BrickRec* __restrict__ bricks, const GridDesc* __restrict__ desc, const StatusBlock* st,
+                unsigned int* ctl, int K) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ PSlot slots[kPS];
+  constexpr size_t kSlotBytes = (size_t)Op::kTiles * kTileBytes;
+  constexpr int kPW = kPT / 32;
+  pdl_wait();
+  if (batch_failed(st)) return;
+  const int nbricks = desc->nbricks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kPS) mbar_init(&slots[threadIdx.x].full, 1);
+  __syncthreads();
+  // one warp fills the ring IN ORDER: tickets of a CTA must grow with the slot sequence, so that the
+  // first empty slot a warp meets means that every later one is empty too
+  if (warp == 0) {
+#pragma unroll 1
+    for (int s = 0; s < kPS; ++s) persist_refill(op, slots[s], dyn + (size_t)s * kSlotBytes, bricks, nbricks, ctl, lane);
+  }
+  for (int it = 0;; ++it) {
+    const int s = it % kPS;
+    PSlot& sl = slots[s];
+    mbar_wait(&sl.full, (uint32_t)(it / kPS) & 1u);
+    if (sl.brick < 0) break;
+    const unsigned char* ta = dyn + (size_t)s * kSlotBytes;
+    const unsigned char* tb = ta + (Op::kTiles > 1 ? kTileBytes : 0);
+    const int own_n = sl.rec.own_n;
+    // chunks of 32 owned particles; the list row, count and first quad of the NEXT chunk are
+    // requested before the current one is processed (the chain ticket -> count -> list -> gather)
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&sl.next, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    bool have = base + lane < own_n;
+    Owned o{};
+    const uint2* row = nullptr;
+    uint32_t cnt = 0;
+    uint2 first = make_uint2(0u, 0u);
+    if (have) {
+      o = brick_owned(sl.rec, base + lane);
+      row = list_row(nbr, K, o.i);
+      cnt = nbr_count[o.i];
+      first = __ldcs(row);
+    }
+    while (base < own_n) {
+      int nbase = 0;
+      if (lane == 0) nbase = atomicAdd(&sl.next, 32);
+      nbase = __shfl_sync(0xffffffffu, nbase, 0);
+      const bool haven = nbase + lane < own_n;
+      Owned on{};
+      const uint2* rown = nullptr;
+      uint32_t cntn = 0;
+      uint2 firstn = make_uint2(0u, 0u);
+      if (haven) {
+        on = brick_owned(sl.rec, nbase + lane);
+        rown = list_row(nbr, K, on.i);
+        cntn = nbr_count[on.i];
+        firstn = __ldcs(rown);
+      }
+      if (have) op.particle(o, row, cnt, first, ta, tb);
+      base = nbase;
+      have = haven;
+      o = on;
+      row = rown;
+      cnt = cntn;
+      first = firstn;
+    }
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      last = atomicAdd(&sl.left, 1) == kPW - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence_block();
+      persist_refill(op, sl, dyn + (size_t)s * kSlotBytes, bricks, nbricks, ctl, lane);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(ctl + 1, gridDim.x - 1) == gridDim.x - 1) {
+      __threadfence();
+      ctl[0] = 0u;
+    }
+  }
 }
 
 // <<<grid, block, smem, stream>>> with the optional programmatic-serialization attribute of PBF_LAUNCH
@@ -587,25 +763,66 @@ static inline bool common_case(const StepConsts& c) {
 }  // namespace
 
 // ================================================================== launchers
+namespace {
+
+int g_sms = 0;
+bool g_persist = true;
+
+template <typename Op>
+cudaError_t opt_in_op() {
+  constexpr size_t once = (size_t)Op::kTiles * kTileBytes, ring = (size_t)kPS * once;
+  cudaError_t e = opt_in(k_brick_once<Op>, once);
+  if (e != cudaSuccess) return e;
+  if (!g_persist) return e;
+  if constexpr (Op::kTiles == 1) return opt_in(k_brick_persist<Op, PBF_PERSIST_THREADS, 2>, ring);
+  else return opt_in(k_brick_persist<Op, PBF_PERSIST_THREADS2, 1>, ring);
+}
+
+// Runs one pass over every brick with the driver selected at start-up.
+template <typename Op>
+void run_pass(const Op& op, const NeighborList& nl, const StatusBlock* st, cudaStream_t s) {
+  const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
+  if (g_persist) {
+    constexpr size_t ring = (size_t)kPS * Op::kTiles * kTileBytes;
+    if constexpr (Op::kTiles == 1)
+      launch_smem(k_brick_persist<Op, PBF_PERSIST_THREADS, 2>, 2 * g_sms, PBF_PERSIST_THREADS, ring, s, op, idx, nl.count,
+                  nl.bricks, nl.desc, st, nl.brick_ctl, nl.K);
+    else
+      launch_smem(k_brick_persist<Op, PBF_PERSIST_THREADS2, 1>, g_sms, PBF_PERSIST_THREADS2, ring, s, op, idx, nl.count,
+                  nl.bricks, nl.desc, st, nl.brick_ctl, nl.K);
+  } else {
+    launch_smem(k_brick_once<Op>, nl.brick_cap, Op::kTiles == 1 ? kBT : kBT2, (size_t)Op::kTiles * kTileBytes, s, op, idx,
+                nl.count, nl.bricks, nl.desc, st, nl.K);
+  }
+}
+
+}  // namespace
+
+// PBF_BRICK_PERSIST=0 selects the one-CTA-per-brick driver (A/B runs); default: persistent CTAs.
 int brick_setup() {
-  cudaError_t e = cudaSuccess;
+  if (const char* env = std::getenv("PBF_BRICK_PERSIST")) g_persist = env[0] != '0';
+  // a ring must fit one SM (one-tile passes run two CTAs per SM)
+  if ((size_t)kPS * kTileBytes * 2 > 220u * 1024u) g_persist = false;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  chk(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   chk(opt_in(k_neighbors_brick, kTileBytes));
-  chk(opt_in(k_lambda_brick<true, true>, kTileBytes));
-  chk(opt_in(k_lambda_brick<true, false>, kTileBytes));
-  chk(opt_in(k_lambda_brick<false, false>, kTileBytes));
-  chk(opt_in(k_delta_brick<true, false, true>, kTileBytes));
-  chk(opt_in(k_delta_brick<true, true, true>, kTileBytes));
-  chk(opt_in(k_delta_brick<true, false, false>, kTileBytes));
-  chk(opt_in(k_delta_brick<true, true, false>, kTileBytes));
-  chk(opt_in(k_delta_brick<false, false, false>, kTileBytes));
-  chk(opt_in(k_delta_brick<false, true, false>, kTileBytes));
-  chk(opt_in(k_xsph_brick<true>, 2 * kTileBytes));
-  chk(opt_in(k_xsph_brick<false>, 2 * kTileBytes));
-  chk(opt_in(k_vort_omega_brick<true>, 2 * kTileBytes));
-  chk(opt_in(k_vort_omega_brick<false>, 2 * kTileBytes));
-  chk(opt_in(k_vort_apply_brick<true>, kTileBytes));
-  chk(opt_in(k_vort_apply_brick<false>, kTileBytes));
+  chk(opt_in_op<LambdaOp<true, true>>());
+  chk(opt_in_op<LambdaOp<true, false>>());
+  chk(opt_in_op<LambdaOp<false, false>>());
+  chk(opt_in_op<DeltaOp<true, false, true>>());
+  chk(opt_in_op<DeltaOp<true, true, true>>());
+  chk(opt_in_op<DeltaOp<true, false, false>>());
+  chk(opt_in_op<DeltaOp<true, true, false>>());
+  chk(opt_in_op<DeltaOp<false, false, false>>());
+  chk(opt_in_op<DeltaOp<false, true, false>>());
+  chk(opt_in_op<XsphOp<true>>());
+  chk(opt_in_op<XsphOp<false>>());
+  chk(opt_in_op<OmegaOp<true>>());
+  chk(opt_in_op<OmegaOp<false>>());
+  chk(opt_in_op<EtaOp<true>>());
+  chk(opt_in_op<EtaOp<false>>());
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -623,31 +840,26 @@ int launch_neighbors_brick(const float4* pred_s, const StepConsts& c, const Grid
 
 int launch_lambda_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool strict,
                         cudaStream_t s) {
-  const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
   if (strict && c.sqrt_safe)
-    launch_smem(k_lambda_brick<true, true>, nl.brick_cap, kBT, kTileBytes, s, b.pred[cur], idx, nl.count, b.rho, nl.bricks, nl.desc, c,
-                b.status, b.dbg, nl.K);
+    run_pass(LambdaOp<true, true>{b.pred[cur], b.rho, c, b.dbg}, nl, b.status, s);
   else if (strict)
-    launch_smem(k_lambda_brick<true, false>, nl.brick_cap, kBT, kTileBytes, s, b.pred[cur], idx, nl.count, b.rho, nl.bricks, nl.desc, c,
-                b.status, b.dbg, nl.K);
+    run_pass(LambdaOp<true, false>{b.pred[cur], b.rho, c, b.dbg}, nl, b.status, s);
   else
-    launch_smem(k_lambda_brick<false, false>, nl.brick_cap, kBT, kTileBytes, s, b.pred[cur], idx, nl.count, b.rho, nl.bricks, nl.desc, c,
-                b.status, b.dbg, nl.K);
+    run_pass(LambdaOp<false, false>{b.pred[cur], b.rho, c, b.dbg}, nl, b.status, s);
   return 1;
 }
 
 template <bool S, bool COMMON>
 static void delta_brick_impl(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
                              bool is_final, cudaStream_t s) {
-  const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
   if (last)
-    launch_smem(k_delta_brick<S, true, COMMON>, nl.brick_cap, kBT, kTileBytes, s, b.pred[cur], b.pred[cur ^ 1], idx, nl.count,
-                b.pos_s, b.rho, b.vel[0], b.planes, b.pos_o, b.vel_o, nl.bricks, nl.desc, c, b.status, b.dbg, b.halo,
-                is_final ? 1 : 0, nl.K);
+    run_pass(DeltaOp<S, true, COMMON>{b.pred[cur], b.pred[cur ^ 1], b.pos_s, b.rho, b.vel[0], b.planes, b.pos_o, b.vel_o, c,
+                                      b.dbg, b.halo, is_final ? 1 : 0},
+             nl, b.status, s);
   else
-    launch_smem(k_delta_brick<S, false, COMMON>, nl.brick_cap, kBT, kTileBytes, s, b.pred[cur], b.pred[cur ^ 1], idx, nl.count,
-                b.pos_s, b.rho, b.vel[0], b.planes, b.pos_o, b.vel_o, nl.bricks, nl.desc, c, b.status, b.dbg, b.halo, 0,
-                nl.K);
+    run_pass(DeltaOp<S, false, COMMON>{b.pred[cur], b.pred[cur ^ 1], b.pos_s, b.rho, b.vel[0], b.planes, b.pos_o, b.vel_o, c,
+                                       b.dbg, b.halo, 0},
+             nl, b.status, s);
 }
 
 int launch_delta_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int cur, bool last,
@@ -660,37 +872,28 @@ int launch_delta_brick(const SolveBuffers& b, const NeighborList& nl, const Step
 
 int launch_xsph_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, bool is_final,
                       bool strict, cudaStream_t s) {
-  const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
   if (strict)
-    launch_smem(k_xsph_brick<true>, nl.brick_cap, kBT2, 2 * kTileBytes, s, pos, b.vel[0], b.vel[1], idx, nl.count, b.pos_s,
-                b.planes, b.pos_o, b.vel_o, nl.bricks, nl.desc, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K);
+    run_pass(XsphOp<true>{pos, b.vel[0], b.vel[1], b.pos_s, b.planes, b.pos_o, b.vel_o, c, b.dbg, b.halo, is_final ? 1 : 0},
+             nl, b.status, s);
   else
-    launch_smem(k_xsph_brick<false>, nl.brick_cap, kBT2, 2 * kTileBytes, s, pos, b.vel[0], b.vel[1], idx, nl.count, b.pos_s,
-                b.planes, b.pos_o, b.vel_o, nl.bricks, nl.desc, c, b.status, b.dbg, b.halo, is_final ? 1 : 0, nl.K);
+    run_pass(XsphOp<false>{pos, b.vel[0], b.vel[1], b.pos_s, b.planes, b.pos_o, b.vel_o, c, b.dbg, b.halo, is_final ? 1 : 0},
+             nl, b.status, s);
   return 1;
 }
 
 int launch_vort_omega_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
                             bool strict, cudaStream_t s) {
-  const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
-  if (strict)
-    launch_smem(k_vort_omega_brick<true>, nl.brick_cap, kBT2, 2 * kTileBytes, s, pos, b.vel[vcur], b.omega, idx, nl.count,
-                nl.bricks, nl.desc, c, b.status, nl.K);
-  else
-    launch_smem(k_vort_omega_brick<false>, nl.brick_cap, kBT2, 2 * kTileBytes, s, pos, b.vel[vcur], b.omega, idx, nl.count,
-                nl.bricks, nl.desc, c, b.status, nl.K);
+  if (strict) run_pass(OmegaOp<true>{pos, b.vel[vcur], b.omega, c}, nl, b.status, s);
+  else run_pass(OmegaOp<false>{pos, b.vel[vcur], b.omega, c}, nl, b.status, s);
   return 1;
 }
 
 int launch_vort_apply_brick(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, float4* pos, int vcur,
                             bool strict, cudaStream_t s) {
-  const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
   if (strict)
-    launch_smem(k_vort_apply_brick<true>, nl.brick_cap, kBT, kTileBytes, s, pos, b.vel[vcur], b.omega, idx, nl.count, b.pos_s,
-                b.planes, b.pos_o, b.vel_o, nl.bricks, nl.desc, c, b.status, b.dbg, nl.K);
+    run_pass(EtaOp<true>{pos, b.vel[vcur], b.omega, b.pos_s, b.planes, b.pos_o, b.vel_o, c, b.dbg}, nl, b.status, s);
   else
-    launch_smem(k_vort_apply_brick<false>, nl.brick_cap, kBT, kTileBytes, s, pos, b.vel[vcur], b.omega, idx, nl.count, b.pos_s,
-                b.planes, b.pos_o, b.vel_o, nl.bricks, nl.desc, c, b.status, b.dbg, nl.K);
+    run_pass(EtaOp<false>{pos, b.vel[vcur], b.omega, b.pos_s, b.planes, b.pos_o, b.vel_o, c, b.dbg}, nl, b.status, s);
   return 1;
 }
 

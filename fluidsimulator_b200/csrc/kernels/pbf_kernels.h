@@ -54,6 +54,7 @@ struct NeighborList {
   const BrickRec* bricks = nullptr;
   const GridDesc* desc = nullptr;
   int brick_cap = 0;
+  unsigned int* brick_ctl = nullptr;  // persistent brick kernels: {brick ticket, finished CTAs}, zero between launches
 };
 
 // SoA host staging <-> float4 persistent state

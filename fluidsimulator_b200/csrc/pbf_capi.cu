@@ -172,6 +172,10 @@ int ensure_tables(pbf_ctx* ctx) {
       invalidate_graph(ctx);
       PBF_CUDA(ctx, ctx->bricks.reserve((size_t)ctx->brick_cap));
     }
+    if (!ctx->brick_ctl.p) {
+      invalidate_graph(ctx);
+      PBF_CUDA(ctx, ctx->brick_ctl.reserve(2));
+    }
   }
   if (ctx->debug) {
     PBF_CUDA(ctx, ctx->dbg_lambda.reserve(slots));
@@ -249,6 +253,7 @@ void fill_neighbor_list(pbf_ctx* ctx, NeighborList& nl) {
   nl.bricks = ctx->brick_on ? ctx->bricks.p : nullptr;
   nl.desc = ctx->desc.p;
   nl.brick_cap = ctx->brick_on ? ctx->brick_cap : 0;
+  nl.brick_ctl = ctx->brick_on ? ctx->brick_ctl.p : nullptr;
 }
 
 void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
@@ -367,6 +372,8 @@ int reset_status(pbf_ctx* ctx) {
   for (int a = 0; a < 3; ++a) { z.min_cell[a] = INT_MAX; z.max_cell[a] = INT_MIN; }
   *ctx->status_host = z;
   PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status.p, ctx->status_host, sizeof(StatusBlock), cudaMemcpyHostToDevice, ctx->stream));
+  // ticket / exit counter of the persistent brick kernels (they leave both at zero themselves)
+  if (ctx->brick_ctl.p) PBF_CUDA(ctx, cudaMemsetAsync(ctx->brick_ctl.p, 0, 2 * sizeof(unsigned int), ctx->stream));
   // The per-cell counters are zero between substeps and a sparse table is wiped by the next
   // k_predict; only fresh allocations and a batch that failed half-way need a reset here.
   if (ctx->tables_dirty && ctx->cell_count.p) {
@@ -485,6 +492,7 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->cell_count.release(); ctx->cell_excl.release(); ctx->slot_id.release(); ctx->cell_key.release();
   ctx->chunk_total.release(); ctx->cell_range.release(); ctx->nbr_idx.release(); ctx->nbr_count.release();
   ctx->bricks.release();
+  ctx->brick_ctl.release();
   for (auto& b : ctx->soa) b.release();
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
   ctx->dbg_dv.release(); ctx->dbg_eta.release();

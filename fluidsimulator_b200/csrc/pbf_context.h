@@ -160,6 +160,7 @@ struct pbf_ctx {
   // tiles do not fit (or that needs the sparse cell table) is replayed with the global-gather family
   // and the brick path is tried again `brick_retry` batches later.
   pbf::DevBuf<pbf::BrickRec> bricks;
+  pbf::DevBuf<unsigned int> brick_ctl;  // {brick ticket, finished CTAs} of the persistent brick kernels
   int brick_cap = 0;
   bool brick_want = true, brick_on = false;
   int brick_retry = 0;
