@@ -17,6 +17,7 @@ LIB_PATH = _PKG / "lib" / "libpbf_b200.so"
 
 PBF_MODE_STRICT = 0
 PBF_MODE_FAST = 1
+PBF_BRICK_OFF, PBF_BRICK_PERSISTENT, PBF_BRICK_PER_CTA = 0, 1, 2
 
 SCRATCH_IDS = {
     "pred_x": 0, "pred_y": 1, "pred_z": 2,
@@ -255,9 +256,10 @@ class Solver:
     def set_graph(self, enabled: bool):
         self._check(self.lib.pbf_set_graph(self.ctx, int(enabled)))
 
-    def set_brick(self, enabled: bool):
-        """Brick kernels (shared-memory staged neighbourhoods, default) or the global-gather family."""
-        self._check(self.lib.pbf_set_brick(self.ctx, int(enabled)))
+    def set_brick(self, mode: int):
+        """PBF_BRICK_OFF (global-gather kernels, default), PBF_BRICK_PERSISTENT or PBF_BRICK_PER_CTA
+        (shared-memory staged bricks).  Same results bit for bit."""
+        self._check(self.lib.pbf_set_brick(self.ctx, int(mode)))
 
     def brick_status(self) -> dict:
         """Whether the last batch ran on the brick path, batches replayed without it, largest tile."""

@@ -766,14 +766,14 @@ static inline bool common_case(const StepConsts& c) {
 namespace {
 
 int g_sms = 0;
-bool g_persist = true;
+bool g_ring_fits = true;  // a ring of kPS slots fits one SM twice (one-tile passes run two CTAs per SM)
 
 template <typename Op>
 cudaError_t opt_in_op() {
   constexpr size_t once = (size_t)Op::kTiles * kTileBytes, ring = (size_t)kPS * once;
   cudaError_t e = opt_in(k_brick_once<Op>, once);
   if (e != cudaSuccess) return e;
-  if (!g_persist) return e;
+  if (!g_ring_fits) return e;
   if constexpr (Op::kTiles == 1) return opt_in(k_brick_persist<Op, PBF_PERSIST_THREADS, 2>, ring);
   else return opt_in(k_brick_persist<Op, PBF_PERSIST_THREADS2, 1>, ring);
 }
@@ -782,7 +782,7 @@ cudaError_t opt_in_op() {
 template <typename Op>
 void run_pass(const Op& op, const NeighborList& nl, const StatusBlock* st, cudaStream_t s) {
   const uint16_t* idx = reinterpret_cast<const uint16_t*>(nl.idx);
-  if (g_persist) {
+  if (nl.brick_persist && g_ring_fits) {
     constexpr size_t ring = (size_t)kPS * Op::kTiles * kTileBytes;
     if constexpr (Op::kTiles == 1)
       launch_smem(k_brick_persist<Op, PBF_PERSIST_THREADS, 2>, 2 * g_sms, PBF_PERSIST_THREADS, ring, s, op, idx, nl.count,
@@ -798,11 +798,8 @@ void run_pass(const Op& op, const NeighborList& nl, const StatusBlock* st, cudaS
 
 }  // namespace
 
-// PBF_BRICK_PERSIST=0 selects the one-CTA-per-brick driver (A/B runs); default: persistent CTAs.
 int brick_setup() {
-  if (const char* env = std::getenv("PBF_BRICK_PERSIST")) g_persist = env[0] != '0';
-  // a ring must fit one SM (one-tile passes run two CTAs per SM)
-  if ((size_t)kPS * kTileBytes * 2 > 220u * 1024u) g_persist = false;
+  if ((size_t)kPS * kTileBytes * 2 > 220u * 1024u) g_ring_fits = false;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };

@@ -55,6 +55,7 @@ struct NeighborList {
   const GridDesc* desc = nullptr;
   int brick_cap = 0;
   unsigned int* brick_ctl = nullptr;  // persistent brick kernels: {brick ticket, finished CTAs}, zero between launches
+  bool brick_persist = true;          // persistent CTAs with a ring of tile slots (false: one CTA per brick)
 };
 
 // SoA host staging <-> float4 persistent state

@@ -254,6 +254,7 @@ void fill_neighbor_list(pbf_ctx* ctx, NeighborList& nl) {
   nl.desc = ctx->desc.p;
   nl.brick_cap = ctx->brick_on ? ctx->brick_cap : 0;
   nl.brick_ctl = ctx->brick_on ? ctx->brick_ctl.p : nullptr;
+  nl.brick_persist = ctx->brick_persist;
 }
 
 void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
@@ -465,7 +466,10 @@ pbf_ctx* pbf_create(int device, size_t capacity) {
     return nullptr;
   }
   ctx->stream = ctx->own_stream;
-  if (const char* env = std::getenv("PBF_BRICK")) ctx->brick_want = env[0] != '0';
+  if (const char* env = std::getenv("PBF_BRICK")) {  // 0 = global gather, 1 = persistent bricks, 2 = one CTA per brick
+    ctx->brick_want = env[0] != '0';
+    ctx->brick_persist = env[0] != '2';
+  }
   if (const int brc = brick_setup()) {
     g_error = std::string("pbf_create: shared-memory opt-in of the brick kernels failed: ") + cudaGetErrorString((cudaError_t)brc);
     pbf_destroy(ctx);
@@ -944,11 +948,16 @@ int pbf_debug_set_capacity(pbf_ctx* ctx, int K, uint32_t cell_cap) {
   return PBF_OK;
 }
 
-// 1 = one CTA per brick of grid cells with shared-memory staged neighbourhoods (default, unless the
-// environment says PBF_BRICK=0), 0 = the global-gather kernels.  Same results bit for bit.
-int pbf_set_brick(pbf_ctx* ctx, int enabled) {
-  if (!ctx) return PBF_E_INVALID;
-  ctx->brick_want = enabled != 0;
+// Kernel family of the passes that walk the neighbour list (same results bit for bit):
+// PBF_BRICK_OFF = global-gather kernels (default: measured faster on B200),
+// PBF_BRICK_PERSISTENT / PBF_BRICK_PER_CTA = shared-memory staged bricks.  Environment PBF_BRICK=0|1|2
+// sets the initial choice of a context.
+int pbf_set_brick(pbf_ctx* ctx, int mode) {
+  if (!ctx || mode < PBF_BRICK_OFF || mode > PBF_BRICK_PER_CTA) return PBF_E_INVALID;
+  const bool want = mode != PBF_BRICK_OFF, persist = mode != PBF_BRICK_PER_CTA;
+  if (want && persist != ctx->brick_persist) invalidate_graph(ctx);
+  ctx->brick_want = want;
+  if (want) ctx->brick_persist = persist;
   ctx->brick_retry = 0;
   return PBF_OK;
 }

@@ -60,6 +60,8 @@ struct Transport {
   // all-reduce of a small host array over all slabs (op 0 = max, 1 = sum); blocking, collective
   virtual int allreduce_host(pbf_ctx* ctx, long long* words, int count, int op) = 0;
   virtual void abort() {}
+  // a batch was replayed because a neighbour's flag timed out: wait longer next time
+  virtual void relax_timeout() {}
   // true when exchange() is purely stream-ordered, i.e. may be recorded into a CUDA graph
   virtual bool capturable() const { return false; }
   // Called at the start of every slab batch attempt, before anything is enqueued: (re)establish
@@ -162,7 +164,8 @@ struct pbf_ctx {
   pbf::DevBuf<pbf::BrickRec> bricks;
   pbf::DevBuf<unsigned int> brick_ctl;  // {brick ticket, finished CTAs} of the persistent brick kernels
   int brick_cap = 0;
-  bool brick_want = true, brick_on = false;
+  bool brick_want = false, brick_on = false;
+  bool brick_persist = true;      // which brick driver: persistent CTAs (PBF_BRICK_PERSISTENT) or one CTA per brick
   int brick_retry = 0;
   uint64_t brick_fallbacks = 0;
   bool last_brick = false;        // the last completed batch ran on the brick path (debug surface)

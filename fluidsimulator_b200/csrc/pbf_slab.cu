@@ -359,8 +359,14 @@ struct PeerMailbox {
 };
 constexpr size_t kMailboxElems = 16;  // float4 elements reserved for the mailbox (256 B)
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void k_peer_signal_wait(PeerMailbox* mine, PeerMailbox* left, PeerMailbox* right, StatusBlock* st,
-                                   long long timeout_cycles) {
+                                   unsigned long long timeout_ns) {
   pdl_wait();
   // All stores of the preceding pack kernel are complete (kernel boundary); the fences order them
   // before the flags at system scope.  Runs even when the batch has failed: a neighbour must never
@@ -371,13 +377,17 @@ __global__ void k_peer_signal_wait(PeerMailbox* mine, PeerMailbox* left, PeerMai
   if (left) *reinterpret_cast<volatile unsigned int*>(&left->arrived[1]) = e;    // I am its right neighbour
   if (right) *reinterpret_cast<volatile unsigned int*>(&right->arrived[0]) = e;  // I am its left neighbour
   __threadfence_system();
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
   for (int side = 0; side < 2; ++side) {
     if (!(side == 0 ? left : right)) continue;
     const volatile unsigned int* flag = &mine->arrived[side];
+    unsigned int spins = 0;
     while ((int)(*flag - e) < 0) {
-      if (clock64() - t0 > timeout_cycles) {  // the neighbour died or diverged: fail the batch, do not hang
-        st->peer_failed = 1;
+      // wall clock (%globaltimer), not SM cycles: the limit must not depend on the clock the GPU runs at.
+      // Never hang: a neighbour that stalled (lazy module load, graph instantiation, a profiler replay, a
+      // shared GPU) or died fails the batch with a retryable flag; slab_step restores and replays it.
+      if ((++spins & 63u) == 0 && global_ns() - t0 > timeout_ns) {
+        st->peer_timeout = 1;
         break;
       }
     }
@@ -401,6 +411,18 @@ struct PeerTransport : Transport {
   // on behalf of one slab synchronises the device and would never return while another slab's
   // flag kernel waits for it.
   bool active = false;
+  // how long a flag kernel waits for a neighbour before it fails the batch (PBF_SLAB_PEER_TIMEOUT_MS,
+  // default 2000 ms; slab_step doubles it for every replay a time-out causes)
+  unsigned long long timeout_ns = 2000ull * 1000000ull;
+  PeerTransport() {
+    if (const char* e = std::getenv("PBF_SLAB_PEER_TIMEOUT_MS")) {
+      const long long ms = std::atoll(e);
+      if (ms > 0) timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
+  }
+  void relax_timeout() override {
+    if (timeout_ns < (1ull << 40)) timeout_ns *= 2;
+  }
 
   ~PeerTransport() override {
     close_remote();
@@ -505,7 +527,7 @@ struct PeerTransport : Transport {
     PeerMailbox* mine = reinterpret_cast<PeerMailbox*>(win);
     PBF_LAUNCH(k_peer_signal_wait, 1, 1, ctx->stream, mine, reinterpret_cast<PeerMailbox*>(remote[0]),
                                                  reinterpret_cast<PeerMailbox*>(remote[1]), ctx->status.p,
-                                                 4000000000LL);
+                                                 timeout_ns);
     return PBF_OK;
   }
   int reduce_status_device(pbf_ctx* ctx, unsigned int* w, int n) override { return inner->reduce_status_device(ctx, w, n); }
@@ -874,15 +896,39 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     PBF_CUDA(ctx, cudaMemcpyAsync(sl.gid_bak.p, sl.gid_o.p, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  for (int attempt = 0; attempt < 32; ++attempt) {
-    if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;
-    if ((rc = ensure_tables(ctx)) != PBF_OK) return rc;
-    if ((rc = sl.transport->prepare(ctx, sl.msg_elems)) != PBF_OK) {  // last: may end in a barrier
-      sl.transport->abort();
-      return rc;
+  // State of the start of the batch back into place (device arrays and the owned count).
+  auto restore = [&]() -> cudaError_t {
+    cudaError_t e = cudaSuccess;
+    if (n0) {
+      auto cp = [&](void* d, const void* s, size_t bytes) {
+        const cudaError_t r = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = r;
+      };
+      cp(ctx->pos_o.p, ctx->pos_bak.p, n0 * sizeof(float4));
+      cp(ctx->vel_o.p, ctx->vel_bak.p, n0 * sizeof(float4));
+      cp(sl.gid_o.p, sl.gid_bak.p, n0 * sizeof(uint32_t));
     }
-    if ((rc = reset_status(ctx)) != PBF_OK) return rc;
-    if ((rc = set_device_count(ctx, (int)n0)) != PBF_OK) return rc;
+    ctx->n = n0;
+    return e;
+  };
+  // Every failure after the batch has started leaves through here: the context keeps the state it
+  // had before the call (like the single-GPU path) and the other ranks are released from whatever
+  // exchange or reduction they are waiting in.
+  auto bail = [&](int code) -> int {
+    invalidate_graph(ctx);
+    ctx->tables_dirty = true;
+    restore();
+    cudaStreamSynchronize(ctx->stream);
+    sl.transport->abort();
+    return code;
+  };
+  int timeouts = 0;
+  for (int attempt = 0; attempt < 32; ++attempt) {
+    if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return bail(rc);
+    if ((rc = ensure_tables(ctx)) != PBF_OK) return bail(rc);
+    if ((rc = sl.transport->prepare(ctx, sl.msg_elems)) != PBF_OK) return bail(rc);  // last: may end in a barrier
+    if ((rc = reset_status(ctx)) != PBF_OK) return bail(rc);
+    if ((rc = set_device_count(ctx, (int)n0)) != PBF_OK) return bail(rc);
     // Stream-ordered transports (NCCL) let the whole substep, exchanges included, replay as one
     // CUDA graph.  The first batch after joining the communicator runs un-captured so that NCCL
     // can set up its peer connections outside a capture.
@@ -898,26 +944,28 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
           const int k = slab_substep(ctx);
           const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &gr);
           std::memcpy(ctx->timer.launches, saved, sizeof(saved));
-          if (k < 0) return k;
-          PBF_CUDA(ctx, ce);
+          if (k < 0) {
+            if (gr) cudaGraphDestroy(gr);
+            return bail(k);
+          }
+          if (ce != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, std::string("slab batch: graph capture: ") + cudaGetErrorString(ce)));
           ctx->graph_kernels = k;
           sl.graph_exchanges = sl.exchanges - ex0;
           sl.graph_bytes = sl.bytes_sent - by0;
           sl.exchanges = ex0;
           sl.bytes_sent = by0;
-          PBF_CUDA(ctx, cudaGraphInstantiate(&ctx->graph_exec, gr, 0));
+          const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, gr, 0);
           cudaGraphDestroy(gr);
+          if (ie != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, std::string("slab batch: graph instantiation: ") + cudaGetErrorString(ie)));
         }
-        PBF_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        const cudaError_t le = cudaGraphLaunch(ctx->graph_exec, ctx->stream);
+        if (le != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, std::string("slab batch: graph launch: ") + cudaGetErrorString(le)));
         ctx->launch_count += (uint64_t)ctx->graph_kernels;
         sl.exchanges += sl.graph_exchanges;
         sl.bytes_sent += sl.graph_bytes;
       } else {
         const int k = slab_substep(ctx);
-        if (k < 0) {
-          sl.transport->abort();
-          return k;
-        }
+        if (k < 0) return bail(k);
         ctx->launch_count += (uint64_t)k;
       }
     }
@@ -926,19 +974,19 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       slab_fill(ctx, sb);
       ctx->launch_count += (uint64_t)launch_slab_report(sb, sl.rank, ctx->stream);
     }
-    PBF_CUDA(ctx, cudaGetLastError());
-    unsigned int* dev_words = &ctx->status.p->max_neighbors;
-    if ((rc = sl.transport->reduce_status_device(ctx, dev_words, kStatusShared)) != PBF_OK) return rc;
-    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->status_host, ctx->status.p, sizeof(StatusBlock), cudaMemcpyDeviceToHost, ctx->stream));
-    PBF_CUDA(ctx, cudaMemcpyAsync(&ctx->last_desc, ctx->desc.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, ctx->stream));
-    PBF_CUDA(ctx, cudaMemcpyAsync(sl.counts_host, sl.counts.p, sizeof(SlabCounts), cudaMemcpyDeviceToHost, ctx->stream));
-    const cudaError_t se = cudaStreamSynchronize(ctx->stream);
-    if (se != cudaSuccess) {
-      sl.transport->abort();
-      return fail(ctx, PBF_E_CUDA, std::string("slab batch: ") + cudaGetErrorString(se));
+    {
+      const cudaError_t ge = cudaGetLastError();
+      if (ge != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, std::string("slab batch: ") + cudaGetErrorString(ge)));
     }
+    unsigned int* dev_words = &ctx->status.p->max_neighbors;
+    if ((rc = sl.transport->reduce_status_device(ctx, dev_words, kStatusShared)) != PBF_OK) return bail(rc);
+    cudaError_t se = cudaMemcpyAsync(ctx->status_host, ctx->status.p, sizeof(StatusBlock), cudaMemcpyDeviceToHost, ctx->stream);
+    if (se == cudaSuccess) se = cudaMemcpyAsync(&ctx->last_desc, ctx->desc.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, ctx->stream);
+    if (se == cudaSuccess) se = cudaMemcpyAsync(sl.counts_host, sl.counts.p, sizeof(SlabCounts), cudaMemcpyDeviceToHost, ctx->stream);
+    if (se == cudaSuccess) se = cudaStreamSynchronize(ctx->stream);
+    if (se != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, std::string("slab batch: ") + cudaGetErrorString(se)));
     if (ctx->profile) timer_resolve(ctx);
-    if ((rc = sl.transport->reduce_status_host(ctx, &ctx->status_host->max_neighbors, kStatusShared)) != PBF_OK) return rc;
+    if ((rc = sl.transport->reduce_status_host(ctx, &ctx->status_host->max_neighbors, kStatusShared)) != PBF_OK) return bail(rc);
     const StatusBlock st = *ctx->status_host;
     ctx->last_status = st;
     if (std::getenv("PBF_SLAB_DEBUG"))
@@ -951,12 +999,28 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     const unsigned actionable = st.grid_overflow | st.nbr_overflow | st.mig_overflow | st.ghost_overflow |
                                 st.own_overflow | st.far_migrant;
     if (!actionable && st.peer_failed)
-      return fail(ctx, PBF_E_COMM, "pbf_step: a neighbouring slab reported a failed batch but no rank knows why");
+      return bail(fail(ctx, PBF_E_COMM, "pbf_step: a neighbouring slab reported a failed batch but no rank knows why"));
+    if (!actionable && st.peer_timeout) {
+      // A neighbour's flag did not arrive in time and nothing else is wrong: a transient stall
+      // (lazy module load, graph instantiation, profiler replay, a shared GPU).  The flag is
+      // max-reduced, so every rank restores the batch and replays it with a longer limit.
+      if (++timeouts > 3)
+        return bail(fail(ctx, PBF_E_COMM, "pbf_step: a neighbouring slab did not answer within the peer time-out (4 attempts)"));
+      sl.transport->relax_timeout();
+      invalidate_graph(ctx);  // the limit is a kernel parameter of the captured substep
+      ctx->batches_retried++;
+      ctx->tables_dirty = true;
+      if (restore() != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, "slab batch: restoring the backup failed"));
+      continue;
+    }
     if (!actionable) {
       ctx->n = (size_t)sl.counts_host->n_own;
       for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
       sl.warm = true;
-      if ((rc = maybe_rebalance(ctx, st)) != PBF_OK) return rc;
+      if ((rc = maybe_rebalance(ctx, st)) != PBF_OK) {  // the batch itself is complete: keep its result
+        sl.transport->abort();
+        return rc;
+      }
       // Messages are sent at full capacity (their size is not known to the host), so capacities
       // follow the observed maxima down as well as up.  The maxima are max-reduced over the slabs:
       // every rank takes the same decision.
@@ -977,7 +1041,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     if (st.grid_overflow) {
       const unsigned long long max_cells = ((unsigned long long)st.max_cells_hi << 32) | st.max_cells_lo;
       if (max_cells > (1ull << 30))
-        return fail(ctx, PBF_E_CAPACITY, "pbf_step: bounding grid of a slab needs more than 2^30 cells (diverged or non-finite positions)");
+        return bail(fail(ctx, PBF_E_CAPACITY, "pbf_step: bounding grid of a slab needs more than 2^30 cells (diverged or non-finite positions; state restored to the start of the batch)"));
       uint32_t cap = ctx->cell_cap;
       while ((unsigned long long)cap < max_cells + max_cells / 4) cap <<= 1;
       ctx->cell_cap = cap;
@@ -990,7 +1054,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     const bool other = (st.grid_overflow | st.nbr_overflow | st.mig_overflow | st.ghost_overflow | st.own_overflow) != 0;
     if (st.far_migrant && !other) {
       if (sl.hops >= std::max(1, sl.nranks - 1))
-        return fail(ctx, PBF_E_COMM, "pbf_step: a particle is outside every reachable slab (non-finite position?)");
+        return bail(fail(ctx, PBF_E_COMM, "pbf_step: a particle is outside every reachable slab (non-finite position?)"));
       sl.hops++;
     }
     size_t want = ctx->cap;
@@ -998,15 +1062,11 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
     if (st.own_overflow || st.ghost_overflow) {
       // tot_cap = cap + 2 * gcap must cover max_own (owned + ghosts)
       ctx->cap = 0;  // force the resize below
-      if ((rc = ensure_particles(ctx, want, n0)) != PBF_OK) return rc;
+      if ((rc = ensure_particles(ctx, want, n0)) != PBF_OK) return bail(rc);
     }
-    if (n0) {
-      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-      PBF_CUDA(ctx, cudaMemcpyAsync(sl.gid_o.p, sl.gid_bak.p, n0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
+    if (restore() != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, "slab batch: restoring the backup failed"));
   }
-  return fail(ctx, PBF_E_CAPACITY, "pbf_step: slab tables kept overflowing after 32 growth attempts");
+  return bail(fail(ctx, PBF_E_CAPACITY, "pbf_step: slab tables kept overflowing after 32 growth attempts"));
 }
 
 }  // namespace pbf

@@ -104,13 +104,21 @@ int pbf_set_mode(pbf_ctx* ctx, int mode);
 int pbf_set_stream(pbf_ctx* ctx, void* cuda_stream);
 /* 1 = replay each substep as a CUDA graph (default), 0 = plain stream launches. */
 int pbf_set_graph(pbf_ctx* ctx, int enabled);
-/* Kernel family of the neighbour build and the solver passes.  1 (default; environment PBF_BRICK=0
- * changes it) = one CTA per brick of grid cells, the brick's neighbourhood staged into shared memory
- * by TMA bulk copies, 16-bit tile-relative neighbour lists.  0 = one thread per particle gathering
- * from global memory (what replaces reference cuda_stub.cu:155-416 either way).  Results are
- * bit-identical; a batch the brick path cannot hold (tile capacity, sparse cell table of a diverged
- * scene) is transparently replayed on the other family. */
-int pbf_set_brick(pbf_ctx* ctx, int enabled);
+/* Kernel family of the neighbour build and the passes that walk the neighbour list (what replaces
+ * reference cuda_stub.cu:155-416 either way; results are bit-identical):
+ *   PBF_BRICK_OFF         one thread per particle, neighbours gathered from global memory through L1,
+ *                         32-bit list entries.  Default: measured faster on B200.
+ *   PBF_BRICK_PERSISTENT  bricks of 4x4x4 grid cells; the brick plus one halo cell layer is staged into
+ *                         shared memory by TMA bulk copies, gathers are LDS.128 through 16-bit
+ *                         tile-relative list entries; persistent CTAs with a ring of tile slots.
+ *   PBF_BRICK_PER_CTA     the same with one CTA per brick.
+ * The environment variable PBF_BRICK=0|1|2 sets the initial choice of a context.  A batch the brick
+ * path cannot hold (tile capacity, sparse cell table of a diverged scene) is transparently replayed on
+ * the global-gather family. */
+#define PBF_BRICK_OFF 0
+#define PBF_BRICK_PERSISTENT 1
+#define PBF_BRICK_PER_CTA 2
+int pbf_set_brick(pbf_ctx* ctx, int mode);
 /* Returns 1 if the last pbf_step batch ran on the brick path, 0 if not; optional outputs: batches
  * replayed on the global-gather family so far, largest tile (records) of the last batch. */
 int pbf_brick_status(const pbf_ctx* ctx, uint64_t* fallbacks, uint32_t* max_tile);

@@ -48,6 +48,20 @@ def make_pair(scene, flags, mode=PBF_MODE_STRICT, iterations=None, oracle_kind=N
     return sol, orc, params
 
 
+def make_pair_from(params, planes, state, mode=PBF_MODE_STRICT, debug=True):
+    """(solver, oracle, params) for an explicit parameter set / plane list / state (random clouds)."""
+    orc = Oracle(best_kind())
+    orc.set_params(params)
+    orc.set_planes(planes)
+    orc.set_state(state)
+    sol = Solver(0, len(state[0]), mode)
+    sol.set_params(params)
+    sol.set_planes(planes)
+    sol.debug_enable(debug)
+    sol.upload(state)
+    return sol, orc, params
+
+
 def compare_integers(sol: Solver, orc: Oracle) -> list[str]:
     """Bit-exact gate G1: entries, cell table, neighbour lists."""
     bad = []

@@ -23,6 +23,12 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__warps_eligible.avg.per_cycle_active', 'smsp__issue_active.avg.per_cycle_active',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__data_pipe_lsu_wavefronts_mem_lg.sum', 'sm__cycles_active.avg']
+import re
+want += [h for h in hdr if re.match(r'(sm__inst_executed_pipe_\w+\.avg\.pct_of_peak_sustained_active|sm__pipe_\w+_cycles_active\.avg\.pct_of_peak_sustained_active|'
+                                    r'l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum|l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum|'
+                                    r'l1tex__data_pipe_lsu_wavefronts\.sum|l1tex__lsu_writeback_active\.avg\.pct_of_peak_sustained_elapsed|'
+                                    r'l1tex__data_pipe_lsu_wavefronts\.avg\.pct_of_peak_sustained_elapsed|l1tex__t_.*pct_of_peak_sustained_elapsed|'
+                                    r'smsp__inst_executed_op_shared_ld\.sum|l1tex__f_.*pct.*|l1tex__m_.*pct.*)$', h)]
 ki = hdr.index('Kernel Name')
 seen = set()
 for r in rows[2:]:

@@ -1,8 +1,8 @@
 """Seconds-scale look at the brick path on the GPU box (no torch): fluid_million, stable flags, STRICT.
 ms/substep and per-stage launch times at t0 and settled, the largest tile along the trajectory, how
 many batches fell back to the global-gather family, and the state digest after 280 substeps (must be
-tests/golden/million.json's 0fc7fad13d5e3129).  PBF_B200_LIB selects a variant library, PBF_BRICK=0
-the global-gather family.   python tools/quick_brick.py [chunk]"""
+tests/golden/million.json's 0fc7fad13d5e3129).  PBF_B200_LIB selects a variant library, PBF_BRICK=0|1|2 the
+global-gather family (default) / persistent bricks / one CTA per brick.   python tools/quick_brick.py [chunk]"""
 import sys
 import time
 from pathlib import Path
