@@ -140,6 +140,8 @@ ABI = {
     "pbf_brick_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "pbf_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
     "pbf_download": (C.c_int, [C.c_void_p] + [_f32p] * 6),
+    "pbf_snapshot_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_snapshot_wait": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(_f32p)] * 3 + [C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
     "pbf_step": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pbf_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -164,6 +166,7 @@ ABI = {
     "pbf_slab_download": (C.c_int, [C.c_void_p, _i64p] + [_f32p] * 6),
     "pbf_slab_upload_owned": (C.c_int, [C.c_void_p, C.c_size_t, _i64p] + [_f32p] * 6),
     "pbf_slab_set_p2p": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_slab_transport": (C.c_int, [C.c_void_p]),
     "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
     "pbf_slab_plan_hist": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int, C.c_float, _i32p]),
     "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
@@ -281,6 +284,19 @@ class Solver:
         out = [np.empty(n, dtype=np.float32) for _ in range(6)]
         self._check(self.lib.pbf_download(self.ctx, *[fptr(a) for a in out]))
         return out
+
+    def snapshot_begin(self, slot: int):
+        """Enqueue an asynchronous copy of the positions into the library's pinned buffer `slot`
+        (0 or 1); it travels on its own stream under the next step() batch."""
+        self._check(self.lib.pbf_snapshot_begin(self.ctx, slot))
+
+    def snapshot_wait(self, slot: int):
+        """(pos_x, pos_y, pos_z views of the pinned buffers, time) of the snapshot begun in `slot`."""
+        ptrs = [_f32p() for _ in range(3)]
+        n, t = C.c_size_t(0), C.c_float(0.0)
+        self._check(self.lib.pbf_snapshot_wait(self.ctx, slot, *[C.byref(p) for p in ptrs], C.byref(n), C.byref(t)))
+        arrs = [np.ctypeslib.as_array(p, shape=(n.value,)) if n.value else np.zeros(0, np.float32) for p in ptrs]
+        return arrs, float(t.value)
 
     def step(self, nsteps: int = 1):
         self._check(self.lib.pbf_step(self.ctx, nsteps))
@@ -410,6 +426,12 @@ class SlabSolver(Solver):
 
     def set_p2p(self, enabled: bool):
         self._check(self.lib.pbf_slab_set_p2p(self.ctx, int(enabled)))
+
+    def transport(self) -> str:
+        """Data plane of the halo exchanges of the last batch."""
+        rc = int(self.lib.pbf_slab_transport(self.ctx))
+        self._check(min(rc, 0))
+        return {1: "local-copies", 2: "nccl-messages", 3: "peer-stores"}.get(rc, "unknown")
 
     def owned(self) -> int:
         return int(self.lib.pbf_slab_owned(self.ctx))

@@ -250,6 +250,16 @@ void download_positions(State& state) {
   state.time = pbf_time(b.ctx);
 }
 
+bool snapshots_available() { return backend().group == nullptr; }
+
+void snapshot_begin(int slot) { check(pbf_snapshot_begin(backend().ctx, slot), "pbf_snapshot_begin"); }
+
+Snapshot snapshot_wait(int slot) {
+  Snapshot s;
+  check(pbf_snapshot_wait(backend().ctx, slot, &s.pos_x, &s.pos_y, &s.pos_z, &s.count, &s.time), "pbf_snapshot_wait");
+  return s;
+}
+
 void download(State& state) {
   Backend& b = backend();
   if (b.group)

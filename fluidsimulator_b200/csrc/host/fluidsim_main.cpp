@@ -49,9 +49,16 @@ bool parse_double(const fluid::b200::ParsedOptions& parsed, const char* name, do
 }
 
 // Frames are handed to one writer thread; at most two are in flight, so a slow disk throttles
-// the simulation instead of exhausting memory.
+// the simulation instead of exhausting memory.  A job either owns its arrays (copies of State) or
+// points at one of the backend's two pinned snapshot buffers (`slot` >= 0): that buffer is not
+// reused before wait_slot() has seen the job written.
 struct FrameJob {
   std::vector<float> x, y, z;
+  const float* px = nullptr;
+  const float* py = nullptr;
+  const float* pz = nullptr;
+  std::size_t count = 0;
+  int slot = -1;
   double time = 0.0;
   std::size_t index = 0;
 };
@@ -63,8 +70,14 @@ class AsyncFrames {
   void submit(std::unique_ptr<FrameJob> job) {
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [&] { return queue_.size() < 2; });
+    if (job->slot >= 0) slot_busy_[job->slot] = true;
     queue_.push_back(std::move(job));
     cv_.notify_all();
+  }
+  // blocks until the frame that reads snapshot buffer `slot` is on disk
+  void wait_slot(int slot) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !slot_busy_[slot]; });
   }
   bool finish() {
     {
@@ -90,18 +103,24 @@ class AsyncFrames {
         cv_.notify_all();
       }
       fluid::b200::FrameView view;
-      view.pos_x = job->x.data();
-      view.pos_y = job->y.data();
-      view.pos_z = job->z.data();
-      view.count = job->x.size();
+      view.pos_x = job->px ? job->px : job->x.data();
+      view.pos_y = job->py ? job->py : job->y.data();
+      view.pos_z = job->pz ? job->pz : job->z.data();
+      view.count = job->px ? job->count : job->x.size();
       view.time = job->time;
       if (!writer_.write(view, job->index)) ok_ = false;
+      if (job->slot >= 0) {
+        std::lock_guard<std::mutex> lk(mu_);
+        slot_busy_[job->slot] = false;
+        cv_.notify_all();
+      }
     }
   }
   const fluid::b200::FrameWriter& writer_;
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<std::unique_ptr<FrameJob>> queue_;
+  bool slot_busy_[2] = {false, false};
   bool done_ = false;
   bool ok_ = true;
   std::thread thread_;
@@ -337,6 +356,27 @@ int main(int argc, char** argv) {
   if (devices.size() > 1) std::cout << "slabs=" << devices.size() << std::endl;
 
   AsyncFrames async_frames(frames);
+  // Overlapped output (one device, resident stepping): the positions of a frame are copied into
+  // one of two pinned buffers on a copy stream WHILE the next batch of substeps runs; the frame
+  // goes to the writer thread one batch later.  PBF_BLOCKING_FRAMES=1 keeps the blocking download.
+  const char* blocking_env = std::getenv("PBF_BLOCKING_FRAMES");
+  const bool overlapped = resident && fluid::b200::snapshots_available() && !(blocking_env && blocking_env[0] == '1');
+  int pending_slot = -1;           // snapshot begun but not yet handed to the writer
+  std::size_t pending_index = 0;
+  auto flush_pending = [&]() {
+    if (pending_slot < 0) return;
+    const fluid::b200::Snapshot snap = fluid::b200::snapshot_wait(pending_slot);
+    std::unique_ptr<FrameJob> job(new FrameJob());
+    job->px = snap.pos_x;
+    job->py = snap.pos_y;
+    job->pz = snap.pos_z;
+    job->count = snap.count;
+    job->slot = pending_slot;
+    job->time = snap.time;
+    job->index = pending_index;
+    async_frames.submit(std::move(job));
+    pending_slot = -1;
+  };
   int step = 0;
   while (step < steps) {
     const auto t0 = std::chrono::steady_clock::now();
@@ -354,13 +394,22 @@ int main(int argc, char** argv) {
     if (!resident) {
       fluid::cuda_step(params, state);
     } else {
-      fluid::b200::step_resident(params, batch);
-      if (wants_frame) fluid::b200::download_positions(state);
+      fluid::b200::step_resident(params, batch);   // the previous frame's copy runs under this batch
+      if (overlapped) flush_pending();
+      if (wants_frame && !overlapped) fluid::b200::download_positions(state);
     }
     step = last + 1;
     const auto t1 = std::chrono::steady_clock::now();
     const double step_ms = std::chrono::duration<double, std::milli>(t1 - t0).count() / batch;
-    if (wants_frame) {
+    if (wants_frame && overlapped) {
+      const int slot = static_cast<int>(frame_index & 1);
+      async_frames.wait_slot(slot);                // the frame that used this buffer is on disk
+      fluid::b200::snapshot_begin(slot);
+      pending_slot = slot;
+      pending_index = frame_index;
+      series.add(fluid::b200::device_time(), fluid::b200::frame_filename("frame", frame_index));
+      frame_index++;
+    } else if (wants_frame) {
       std::unique_ptr<FrameJob> job(new FrameJob());
       job->x = state.pos_x;
       job->y = state.pos_y;
@@ -373,6 +422,7 @@ int main(int argc, char** argv) {
     }
     if (debug_print) std::cout << "step_done=" << step << " step_ms=" << step_ms << std::endl;
   }
+  flush_pending();
   if (!async_frames.finish()) {
     std::cerr << "Failed to write VTK frame." << std::endl;
     return 1;

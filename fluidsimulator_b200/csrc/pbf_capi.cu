@@ -501,6 +501,15 @@ void pbf_destroy(pbf_ctx* ctx) {
   ctx->dbg_lambda.release(); ctx->dbg_rho.release(); ctx->dbg_delta.release();
   ctx->dbg_dv.release(); ctx->dbg_eta.release();
   slab_release(ctx);
+  for (auto& sn : ctx->snap) {
+    for (int a = 0; a < 3; ++a) {
+      sn.dev[a].release();
+      if (sn.host[a]) cudaFreeHost(sn.host[a]);
+    }
+    if (sn.ready) cudaEventDestroy(sn.ready);
+    if (sn.done) cudaEventDestroy(sn.done);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto ev : ctx->timer.pool) cudaEventDestroy(ev);
   for (auto ev : ctx->timer.begin) cudaEventDestroy(ev);
   for (auto ev : ctx->timer.end) cudaEventDestroy(ev);
@@ -691,6 +700,63 @@ int pbf_step(pbf_ctx* ctx, int nsteps) {
     }
   }
   return fail(ctx, PBF_E_CAPACITY, "pbf_step: device tables kept overflowing after 32 growth attempts");
+}
+
+// ---- asynchronous frame output (replaces the blocking read of positions at
+// reference app/src/main.cpp:259-273) --------------------------------------------------------------
+int pbf_snapshot_begin(pbf_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 1) return fail(ctx, PBF_E_INVALID, "pbf_snapshot_begin: bad arguments");
+  if (ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_snapshot_begin: not available on a slab context");
+  cudaSetDevice(ctx->device);
+  pbf_ctx::Snapshot& sn = ctx->snap[slot];
+  if (sn.pending) return fail(ctx, PBF_E_INVALID, "pbf_snapshot_begin: the slot still holds a snapshot nobody waited for");
+  const size_t n = ctx->n;
+  if (!ctx->copy_stream) PBF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!sn.ready) {
+    PBF_CUDA(ctx, cudaEventCreateWithFlags(&sn.ready, cudaEventDisableTiming));
+    PBF_CUDA(ctx, cudaEventCreateWithFlags(&sn.done, cudaEventDisableTiming));
+  }
+  if (n > sn.host_cap) {
+    for (int a = 0; a < 3; ++a) {
+      if (sn.host[a]) cudaFreeHost(sn.host[a]);
+      sn.host[a] = nullptr;
+    }
+    sn.host_cap = 0;
+    for (int a = 0; a < 3; ++a) PBF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&sn.host[a]), n * sizeof(float)));
+    sn.host_cap = n;
+  }
+  sn.n = n;
+  sn.time = ctx->time;
+  if (n) {
+    for (int a = 0; a < 3; ++a) PBF_CUDA(ctx, sn.dev[a].reserve(n));
+    // positions of this moment into the slot's own device copy (stream order: after the last batch) ...
+    float* dsoa[6] = {sn.dev[0].p, sn.dev[1].p, sn.dev[2].p, nullptr, nullptr, nullptr};
+    ctx->launch_count += launch_unpack_state(ctx->pos_o.p, ctx->vel_o.p, dsoa, (int)n, ctx->stream);
+    PBF_CUDA(ctx, cudaEventRecord(sn.ready, ctx->stream));
+    // ... and from there to pinned host memory on the copy stream, under whatever the compute stream does next
+    PBF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, sn.ready, 0));
+    for (int a = 0; a < 3; ++a)
+      PBF_CUDA(ctx, cudaMemcpyAsync(sn.host[a], sn.dev[a].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  PBF_CUDA(ctx, cudaEventRecord(sn.done, ctx->copy_stream));
+  sn.pending = true;
+  return PBF_OK;
+}
+
+int pbf_snapshot_wait(pbf_ctx* ctx, int slot, const float** px, const float** py, const float** pz, size_t* n,
+                      float* time) {
+  if (!ctx || slot < 0 || slot > 1) return fail(ctx, PBF_E_INVALID, "pbf_snapshot_wait: bad arguments");
+  pbf_ctx::Snapshot& sn = ctx->snap[slot];
+  if (!sn.pending) return fail(ctx, PBF_E_INVALID, "pbf_snapshot_wait: no snapshot was begun in this slot");
+  cudaSetDevice(ctx->device);
+  PBF_CUDA(ctx, cudaEventSynchronize(sn.done));
+  sn.pending = false;
+  if (px) *px = sn.host[0];
+  if (py) *py = sn.host[1];
+  if (pz) *pz = sn.host[2];
+  if (n) *n = sn.n;
+  if (time) *time = sn.time;
+  return PBF_OK;
 }
 
 int pbf_host_register(pbf_ctx* ctx, void* ptr, size_t bytes) {

@@ -184,6 +184,20 @@ struct pbf_ctx {
   uint64_t graph_key = 0;
   int graph_kernels = 0;
 
+  // Frame snapshots (pbf_snapshot_begin / _wait): positions are unpacked into a device
+  // staging copy on the compute stream and travel to library-owned pinned host buffers on a copy
+  // stream of their own, so the download runs under the next batch of substeps.  Two slots.
+  struct Snapshot {
+    pbf::DevBuf<float> dev[3];
+    float* host[3] = {nullptr, nullptr, nullptr};  // pinned
+    size_t host_cap = 0;
+    size_t n = 0;
+    float time = 0.0f;
+    bool pending = false;
+    cudaEvent_t ready = nullptr, done = nullptr;
+  } snap[2];
+  cudaStream_t copy_stream = nullptr;
+
   pbf::SlabState slab;
 
   pbf::StageTimer timer;

@@ -1291,6 +1291,15 @@ int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi) {
   return PBF_OK;
 }
 
+int pbf_slab_transport(const pbf_ctx* ctx) {
+  if (!ctx || !ctx->slab.enabled || !ctx->slab.transport) return PBF_E_INVALID;
+  if (const PeerTransport* pt = dynamic_cast<const PeerTransport*>(ctx->slab.transport))
+    if (pt->active) return PBF_TRANSPORT_PEER_STORES;
+  const Transport* base = ctx->slab.transport;
+  if (const PeerTransport* pt = dynamic_cast<const PeerTransport*>(base)) base = pt->inner;
+  return dynamic_cast<const NcclTransport*>(base) ? PBF_TRANSPORT_NCCL_MESSAGES : PBF_TRANSPORT_LOCAL_COPIES;
+}
+
 int pbf_slab_stats(const pbf_ctx* ctx, uint64_t* exchanges, uint64_t* bytes_sent, int32_t* ghosts, int32_t* hops) {
   if (!ctx || !ctx->slab.enabled) return PBF_E_INVALID;
   if (exchanges) *exchanges = ctx->slab.exchanges;

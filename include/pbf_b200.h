@@ -123,6 +123,17 @@ int pbf_set_brick(pbf_ctx* ctx, int mode);
  * replayed on the global-gather family so far, largest tile (records) of the last batch. */
 int pbf_brick_status(const pbf_ctx* ctx, uint64_t* fallbacks, uint32_t* max_tile);
 
+/* Asynchronous frame output (device-resident stepping; replaces the blocking read of positions for
+ * the VTK writer at reference app/src/main.cpp:259-273).  pbf_snapshot_begin enqueues, after the
+ * substeps issued so far, a copy of the positions into one of two library-owned pinned host
+ * buffers and returns at once; the copy runs on its own stream under the next pbf_step batch.
+ * pbf_snapshot_wait blocks until that copy has landed and returns the three arrays (original
+ * particle order; valid until the next pbf_snapshot_begin on the same slot), the particle count and
+ * the simulation time of the snapshot.  Not available on slab contexts. */
+int pbf_snapshot_begin(pbf_ctx* ctx, int slot);
+int pbf_snapshot_wait(pbf_ctx* ctx, int slot, const float** px, const float** py, const float** pz,
+                      size_t* n, float* time);
+
 /* Host SoA -> device (the six H2D copies of reference cuda_stub.cu:791-796).
  * Resets nothing else; time is kept (use pbf_set_time). */
 int pbf_upload(pbf_ctx* ctx, size_t n, const float* px, const float* py,
@@ -273,6 +284,11 @@ int pbf_slab_set_rebalance(pbf_ctx* ctx, float threshold);
 uint64_t pbf_slab_rebalance_count(const pbf_ctx* ctx);
 int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py,
                       float* pz, float* vx, float* vy, float* vz);
+/* Which data plane the last pbf_step batch of this slab used for its halo exchanges. */
+#define PBF_TRANSPORT_LOCAL_COPIES 1  /* one process: cudaMemcpyPeerAsync + events */
+#define PBF_TRANSPORT_NCCL_MESSAGES 2 /* ncclSend / ncclRecv between x-neighbours */
+#define PBF_TRANSPORT_PEER_STORES 3   /* pack kernels store into the neighbour's window, flag kernels */
+int pbf_slab_transport(const pbf_ctx* ctx);
 /* Exchanges and bytes sent since creation, ghosts held after the last substep, migration hops. */
 int pbf_slab_stats(const pbf_ctx* ctx, uint64_t* exchanges, uint64_t* bytes_sent,
                    int32_t* ghosts, int32_t* hops);

@@ -17,8 +17,10 @@ FLAGS = ["--steps-per-sec", "120", "--enable-scorr", "--enable-xsph", "--enable-
          "--plane-restitution", "0.05", "--plane-friction", "0.1"]
 
 
-def run(binary, *args):
-    r = subprocess.run([str(binary), *map(str, args)], capture_output=True, text=True)
+def run(binary, *args, env=None):
+    import os
+    r = subprocess.run([str(binary), *map(str, args)], capture_output=True, text=True,
+                       env=None if env is None else dict(os.environ, **env))
     assert r.returncode == 0, r.stderr
     return r.stdout
 
@@ -80,3 +82,21 @@ def test_own_app_slabs_and_batched_output(built, tmp_path):
     assert len(names) == 5 and "slabs=3" in b     # frames after steps 1, 5, 9, 13 + series.pvd
     pick = lambda s: [l for l in s.splitlines() if l.split("=")[0] in ("particle_count", "end_time")]
     assert pick(a) == pick(b)
+
+
+def test_own_app_overlapped_output_equals_blocking(built, tmp_path):
+    """frames leave through two pinned buffers on a copy stream while the next batch of
+    substeps runs (default) — byte-identical to the blocking download (PBF_BLOCKING_FRAMES=1), with
+    enough frames that both buffers are reused several times and with a one-substep batch size."""
+    scene = scenes.SCENES["fluid_large"].write_json(tmp_path / "scene.json")
+    stable = ["--steps-per-sec", "120", "--enable-scorr", "--enable-xsph", "--plane-restitution", "0.05",
+              "--plane-friction", "0.1"]
+    for fps, steps, frames in ((40, 31, 11), (120, 9, 9)):
+        over, block = tmp_path / f"over{fps}", tmp_path / f"block{fps}"
+        a = run(APP, "--scene", scene, "--steps", steps, "--fps", fps, "--output-dir", over, *stable)
+        b = run(APP, "--scene", scene, "--steps", steps, "--fps", fps, "--output-dir", block, *stable,
+                env={"PBF_BLOCKING_FRAMES": "1"})
+        names = same_tree(over, block)
+        assert len(names) == frames + 1
+        pick = lambda s: [l for l in s.splitlines() if l.split("=")[0] in ("particle_count", "end_time")]
+        assert pick(a) == pick(b)

@@ -92,6 +92,35 @@ def test_step_host_contract(built):
         assert H.bit_equal(a, b)
 
 
+def test_snapshot_is_the_state_of_its_moment(built):
+    """pbf_snapshot_begin / _wait (asynchronous frame output): the positions a snapshot returns are
+    those of the substep it was begun after, whatever ran in between; two slots are independent."""
+    sol, orc, params = H.make_pair(SMALL, H.STABLE_FLAGS, debug=False)
+    sol.step(3)
+    orc.step(3)
+    want0 = [a.copy() for a in orc.get_state()[:3]]
+    t0 = sol.time
+    sol.snapshot_begin(0)
+    sol.step(2)
+    orc.step(2)
+    want1 = [a.copy() for a in orc.get_state()[:3]]
+    sol.snapshot_begin(1)
+    sol.step(4)
+    got0, time0 = sol.snapshot_wait(0)
+    got1, time1 = sol.snapshot_wait(1)
+    for a, b in zip(got0, want0):
+        assert H.bit_equal(np.array(a), b)
+    for a, b in zip(got1, want1):
+        assert H.bit_equal(np.array(a), b)
+    assert np.float32(time0) == np.float32(t0) and time1 > time0
+    with pytest.raises(Exception):
+        sol.snapshot_wait(0)          # nothing pending in the slot any more
+    sol.snapshot_begin(0)
+    with pytest.raises(Exception):
+        sol.snapshot_begin(0)         # still pending
+    sol.snapshot_wait(0)
+
+
 def test_empty_state_advances_time(built):
     from fluidsimulator_b200.capi import Solver
     params, planes, st = scenes.load_scene(SMALL)
