@@ -167,6 +167,7 @@ ABI = {
     "pbf_slab_upload_owned": (C.c_int, [C.c_void_p, C.c_size_t, _i64p] + [_f32p] * 6),
     "pbf_slab_set_p2p": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_slab_transport": (C.c_int, [C.c_void_p]),
+    "pbf_slab_payload": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "pbf_slab_plan": (C.c_int, [C.c_size_t, _f32p, C.c_float, C.c_int, _i32p]),
     "pbf_slab_plan_hist": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int, C.c_float, _i32p]),
     "pbf_slab_cuts": (C.c_int, [C.c_void_p, _i32p, _i32p]),
@@ -185,6 +186,23 @@ ABI = {
 _lib = None
 
 
+def _preload_bundled_nccl() -> None:
+    """libpbf_b200.so needs libnccl.so.2; PyTorch ships a newer NCCL than the system one and resolves
+    its own symbols against whichever libnccl.so.2 the process loaded FIRST.  Loading torch's copy
+    before ours (same soname, newer minor version) keeps `import torch` working whether it happens
+    before or after this library is opened.  Harmless when PyTorch / its NCCL wheel is absent."""
+    try:
+        import glob
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []) or []:
+            for f in sorted(glob.glob(os.path.join(d, "lib", "libnccl.so*"))):
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def load_library(path: os.PathLike | None = None) -> C.CDLL:
     """dlopen libpbf_b200.so and type every exported entry point.  Raises if the
     library or any declared symbol is missing (there is no fallback)."""
@@ -198,6 +216,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         raise RuntimeError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C fluidsimulator_b200/csrc`). There is no CPU fallback.")
+    _preload_bundled_nccl()
     lib = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
     for name, (restype, argtypes) in ABI.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
@@ -284,6 +303,14 @@ class Solver:
         out = [np.empty(n, dtype=np.float32) for _ in range(6)]
         self._check(self.lib.pbf_download(self.ctx, *[fptr(a) for a in out]))
         return out
+
+    def host_register(self, arr: np.ndarray):
+        """Page-lock a host array in place (pbf_host_register): copies to and from it then run at
+        full PCIe speed and pbf_step_host can use its single-graph path."""
+        self._check(self.lib.pbf_host_register(self.ctx, C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self.lib.pbf_host_unregister(self.ctx, C.c_void_p(arr.ctypes.data)))
 
     def snapshot_begin(self, slot: int):
         """Enqueue an asynchronous copy of the positions into the library's pinned buffer `slot`
@@ -426,6 +453,12 @@ class SlabSolver(Solver):
 
     def set_p2p(self, enabled: bool):
         self._check(self.lib.pbf_slab_set_p2p(self.ctx, int(enabled)))
+
+    def payload_bytes(self) -> int:
+        """Payload bytes sent to the neighbours during the last substep (capacity-independent)."""
+        v = C.c_uint64(0)
+        self._check(self.lib.pbf_slab_payload(self.ctx, C.byref(v)))
+        return int(v.value)
 
     def transport(self) -> str:
         """Data plane of the halo exchanges of the last batch."""

@@ -581,7 +581,28 @@ inline int grid_for(int n, int threads) { return (n + threads - 1) / threads; }
 
 }  // namespace
 
+// Final positions of a substep straight from the sorted order into the download staging (the
+// cuda_step contract path starts their D2H while XSPH / vorticity still run).
+__global__ void k_scatter_positions(const float4* __restrict__ pos_sorted, const float4* __restrict__ pos_s,
+                                    float* __restrict__ x, float* __restrict__ y, float* __restrict__ z, int n) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pos_sorted[i];
+  const uint32_t orig = __float_as_uint(pos_s[i].w);
+  x[orig] = p.x;
+  y[orig] = p.y;
+  z[orig] = p.z;
+}
+
 // ================================================================== launchers
+int launch_scatter_positions(const float4* pos_sorted, const float4* pos_s, float* x, float* y, float* z, int n,
+                             cudaStream_t s) {
+  if (n <= 0) return 0;
+  PBF_LAUNCH(k_scatter_positions, grid_for(n, kThreads), kThreads, s, pos_sorted, pos_s, x, y, z, n);
+  return 1;
+}
+
 int launch_pack_state(const float* const soa[6], float4* pos_o, float4* vel_o, int n, cudaStream_t s) {
   if (n <= 0) return 0;
   PBF_LAUNCH(k_pack_state, grid_for(n, kThreads), kThreads, s, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5],

@@ -100,7 +100,10 @@ PosVel* xsph_record(const SolveBuffers& b, const StepConsts& c);  // b.pv when X
 typedef void (*StageCallback)(void* user, int stage_id, int begin);
 int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c,
                  int iterations, NRef n, bool strict, cudaStream_t s,
-                 StageCallback cb, void* cb_user);
+                 StageCallback cb, void* cb_user, int phase = 0);
+// positions (sorted order, original id in pos_s.w) -> three SoA arrays in original order
+int launch_scatter_positions(const float4* pos_sorted, const float4* pos_s, float* x, float* y, float* z, int n,
+                             cudaStream_t s);
 // ---- brick path (kernels/brick.cu): the same stages as one CTA per brick of grid cells, halo staged
 // into shared memory with cp.async.bulk, 16-bit tile-relative neighbour entries ------------------
 int brick_setup();  // opt the kernels in to their dynamic shared memory (once per process / device)

@@ -433,25 +433,33 @@ int launch_commit_only(const SolveBuffers& b, const StepConsts& c, NRef n, bool 
   return 1;
 }
 
-// a8..a14 of one substep on a single GPU.
+// a8..a14 of one substep on a single GPU.  phase 0 = everything; 1 = the iteration loop only (after
+// it the positions of the substep are final: pred[iterations & 1], sorted order); 2 = the tail only
+// (XSPH, vorticity, restitution + scatter) — the cuda_step contract path downloads the positions
+// while the tail still runs (pbf_capi.cu).
 int launch_solve(const SolveBuffers& b, const NeighborList& nl, const StepConsts& c, int iterations, NRef n,
-                 bool strict, cudaStream_t s, StageCallback cb, void* user) {
-  if (iterations <= 0) return launch_commit_only(b, c, n, strict, s);
+                 bool strict, cudaStream_t s, StageCallback cb, void* user, int phase) {
+  if (iterations <= 0) return phase == 2 ? 0 : launch_commit_only(b, c, n, strict, s);
   int launches = 0;
   int cur = 0;
   auto stage = [&](int id, int begin) { if (cb) cb(user, id, begin); };
   const bool tail_xsph = c.do_xsph != 0, tail_vort = c.do_vort != 0;
   const bool final_in_delta = !tail_xsph && !tail_vort;
-  for (int it = 0; it < iterations; ++it) {
-    const bool last = (it == iterations - 1);
-    stage(4, 1);
-    launches += launch_lambda(b, nl, c, cur, n, strict, s);
-    stage(4, 0);
-    stage(5, 1);
-    launches += launch_delta(b, nl, c, cur, last, last && final_in_delta, n, strict, s);
-    stage(5, 0);
-    cur ^= 1;
+  if (phase != 2) {
+    for (int it = 0; it < iterations; ++it) {
+      const bool last = (it == iterations - 1);
+      stage(4, 1);
+      launches += launch_lambda(b, nl, c, cur, n, strict, s);
+      stage(4, 0);
+      stage(5, 1);
+      launches += launch_delta(b, nl, c, cur, last, last && final_in_delta, n, strict, s);
+      stage(5, 0);
+      cur ^= 1;
+    }
+  } else {
+    cur = iterations & 1;
   }
+  if (phase == 1) return launches;
   float4* pos = b.pred[cur];  // committed positions, sorted order
   int vcur = 0;
   if (tail_xsph) {

@@ -97,6 +97,10 @@ void invalidate_graph(pbf_ctx* ctx) {
     cudaGraphExecDestroy(ctx->graph_exec);
     ctx->graph_exec = nullptr;
   }
+  if (ctx->host_graph) {
+    cudaGraphExecDestroy(ctx->host_graph);
+    ctx->host_graph = nullptr;
+  }
 }
 
 // Per-particle buffers.  Arrays in ORIGINAL order hold `cap` owned particles; arrays in SORTED order
@@ -279,7 +283,9 @@ void fill_solve_buffers(pbf_ctx* ctx, SolveBuffers& b) {
   }
 }
 
-int enqueue_substep(pbf_ctx* ctx) {
+// phase 0 = the whole substep; 1 = up to and including the last delta pass (positions final);
+// 2 = the tail (XSPH, vorticity, restitution, scatter to original order).
+int enqueue_substep(pbf_ctx* ctx, int phase = 0) {
   const NRef n = nref((int)ctx->n);
   cudaStream_t s = ctx->stream;
   GridBuffers g{};
@@ -289,6 +295,10 @@ int enqueue_substep(pbf_ctx* ctx) {
   const StepConsts& c = ctx->consts;
   StageTimer& t = ctx->timer;
   int launches = 0, k;
+  SolveBuffers b{};
+  fill_solve_buffers(ctx, b);
+  const int iters = ctx->params.solver_iterations;
+  if (phase == 2) return launch_solve(b, nl, c, iters, n, ctx->mode == PBF_MODE_STRICT, s, stage_mark, ctx, 2);
 
   stage_mark(ctx, PBF_STAGE_PREDICT, 1);
   k = launch_predict(ctx->pos_o.p, ctx->vel_o.p, ctx->pred_o.p, c, g, n, false, s);
@@ -318,10 +328,7 @@ int enqueue_substep(pbf_ctx* ctx) {
   stage_mark(ctx, PBF_STAGE_NEIGHBORS, 0);
   t.launches[PBF_STAGE_NEIGHBORS] += k; launches += k;
 
-  SolveBuffers b{};
-  fill_solve_buffers(ctx, b);
-  const int iters = ctx->params.solver_iterations;
-  k = launch_solve(b, nl, c, iters, n, ctx->mode == PBF_MODE_STRICT, s, stage_mark, ctx);
+  k = launch_solve(b, nl, c, iters, n, ctx->mode == PBF_MODE_STRICT, s, stage_mark, ctx, phase);
   // attribute solver launches to their stages
   if (iters > 0) {
     t.launches[PBF_STAGE_LAMBDA] += iters;
@@ -510,6 +517,9 @@ void pbf_destroy(pbf_ctx* ctx) {
     if (sn.done) cudaEventDestroy(sn.done);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (auto ev : ctx->timer.pool) cudaEventDestroy(ev);
   for (auto ev : ctx->timer.begin) cudaEventDestroy(ev);
   for (auto ev : ctx->timer.end) cudaEventDestroy(ev);
@@ -774,8 +784,145 @@ int pbf_host_unregister(pbf_ctx* ctx, void* ptr) {
   return PBF_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+// The cuda_step contract (reference cuda_stub.cu:764-1099: six H2D copies, one substep, six D2H copies)
+// as ONE CUDA graph on page-locked host arrays:
+//     6 x H2D -> pack -> backup -> predict .. last delta pass -+-> XSPH / vorticity -> unpack vel -> 3 x D2H vel -+-> status
+//                                                               +-> scatter pos -> 3 x D2H pos (side branch) ------+
+// The positions of a substep are final after the last delta pass, so their 12 bytes per particle
+// cross PCIe while the tail passes still run.  The host pointers are graph parameters: the graph is
+// re-captured when the caller passes other arrays (the reference application passes the same State
+// every step).  Returns PBF_OK with *done = false when this path does not apply (pageable memory,
+// no tail pass, brick kernels, profiling, graphs off) or when the substep overflowed a device table
+// (state restored): the caller then takes the plain path, which grows the table and replays.
+int step_host_graph(pbf_ctx* ctx, size_t n, float* const host[6], bool* done) {
+  *done = false;
+  const StepConsts& c = ctx->consts;
+  if (!ctx->use_graph || ctx->profile || ctx->slab.enabled || ctx->brick_want || n == 0) return PBF_OK;
+  if (ctx->params.solver_iterations <= 0 || (!c.do_xsph && !c.do_vort)) return PBF_OK;
+  for (int a = 0; a < 6; ++a)
+    if (!is_pinned(host[a])) return PBF_OK;
+  int rc = ensure_particles(ctx, n, 0);
+  if (rc != PBF_OK) return rc;
+  if (n != ctx->n) invalidate_graph(ctx);
+  ctx->n = n;
+  if (ctx->brick_on) {
+    ctx->brick_on = false;
+    invalidate_graph(ctx);
+  }
+  if ((rc = ensure_tables(ctx)) != PBF_OK) return rc;
+  if (!ctx->side_stream) {
+    PBF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    PBF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    PBF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  bool same = ctx->host_graph != nullptr;
+  for (int a = 0; a < 6; ++a) same = same && ctx->host_graph_ptr[a] == host[a];
+  if ((rc = reset_status(ctx)) != PBF_OK) return rc;  // outside the graph: it may have to wipe tables
+  if (!same) {
+    if (ctx->host_graph) {
+      cudaGraphExecDestroy(ctx->host_graph);
+      ctx->host_graph = nullptr;
+    }
+    cudaStream_t s = ctx->stream;
+    cudaGraph_t gr = nullptr;
+    uint64_t saved[PBF_STAGE_COUNT];
+    std::memcpy(saved, ctx->timer.launches, sizeof(saved));
+    PBF_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int k = 0;
+    bool ok = true;
+    auto chk = [&](cudaError_t e) { ok = ok && e == cudaSuccess; };
+    for (int a = 0; a < 6; ++a) chk(cudaMemcpyAsync(ctx->soa[a].p, host[a], n * sizeof(float), cudaMemcpyHostToDevice, s));
+    const float* dsoa[6] = {ctx->soa[0].p, ctx->soa[1].p, ctx->soa[2].p, ctx->soa[3].p, ctx->soa[4].p, ctx->soa[5].p};
+    k += launch_pack_state(dsoa, ctx->pos_o.p, ctx->vel_o.p, (int)n, s);
+    chk(cudaMemcpyAsync(ctx->pos_bak.p, ctx->pos_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    chk(cudaMemcpyAsync(ctx->vel_bak.p, ctx->vel_o.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    k += enqueue_substep(ctx, 1);
+    // side branch: final positions -> SoA staging -> host, under the tail passes
+    chk(cudaEventRecord(ctx->ev_fork, s));
+    chk(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    const float4* pos_final = (ctx->params.solver_iterations & 1) ? ctx->pred_b.p : ctx->pred_a.p;
+    k += launch_scatter_positions(pos_final, ctx->pos_s.p, ctx->soa[0].p, ctx->soa[1].p, ctx->soa[2].p, (int)n, ctx->side_stream);
+    for (int a = 0; a < 3; ++a)
+      chk(cudaMemcpyAsync(host[a], ctx->soa[a].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->side_stream));
+    chk(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    // main branch: the tail, then the velocities
+    k += enqueue_substep(ctx, 2);
+    float* vsoa[6] = {nullptr, nullptr, nullptr, ctx->soa[3].p, ctx->soa[4].p, ctx->soa[5].p};
+    k += launch_unpack_state(ctx->pos_o.p, ctx->vel_o.p, vsoa, (int)n, s);
+    for (int a = 3; a < 6; ++a)
+      chk(cudaMemcpyAsync(host[a], ctx->soa[a].p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    chk(cudaMemcpyAsync(ctx->status_host, ctx->status.p, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
+    chk(cudaMemcpyAsync(&ctx->last_desc, ctx->desc.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, s));
+    chk(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    const cudaError_t ce = cudaStreamEndCapture(s, &gr);
+    std::memcpy(ctx->timer.launches, saved, sizeof(saved));
+    if (!ok || ce != cudaSuccess || !gr) {
+      if (gr) cudaGraphDestroy(gr);
+      cudaGetLastError();
+      return fail(ctx, PBF_E_CUDA, std::string("pbf_step_host: capturing the contract graph failed: ") + cudaGetErrorString(ce));
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&ctx->host_graph, gr, 0);
+    cudaGraphDestroy(gr);
+    if (ie != cudaSuccess) {
+      ctx->host_graph = nullptr;
+      return fail(ctx, PBF_E_CUDA, std::string("pbf_step_host: cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    }
+    ctx->host_graph_kernels = k;
+    for (int a = 0; a < 6; ++a) ctx->host_graph_ptr[a] = host[a];
+  }
+  PBF_CUDA(ctx, cudaGraphLaunch(ctx->host_graph, ctx->stream));
+  PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->launch_count += (uint64_t)ctx->host_graph_kernels;
+  const StatusBlock st = *ctx->status_host;
+  ctx->last_status = st;
+  if (st.grid_overflow || st.nbr_overflow || st.brick_overflow) {
+    // back to the uploaded state; the plain path below finds the same overflow, grows and replays
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->tables_dirty = true;
+    return PBF_OK;
+  }
+  ctx->time += ctx->params.dt;  // core.cpp:614
+  ctx->last_brick = false;
+  *done = true;
+  return PBF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz, int nsteps) {
-  int rc = upload_state(ctx, n, px, py, pz, vx, vy, vz, false);
+  if (!ctx || nsteps < 0) return fail(ctx, PBF_E_INVALID, "pbf_step_host: bad arguments");
+  if (n > 0 && (!px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_step_host: null array");
+  if (!(ctx->params.h > 0.0f)) return fail(ctx, PBF_E_INVALID, "pbf_step: parameters not set (h == 0)");
+  cudaSetDevice(ctx->device);
+  int rc;
+  if (nsteps == 1 && !ctx->slab.enabled && n <= 0x7fffffffu - 64) {
+    float* const host[6] = {px, py, pz, vx, vy, vz};
+    bool done = false;
+    if ((rc = step_host_graph(ctx, n, host, &done)) != PBF_OK) return rc;
+    if (done) return PBF_OK;
+    if (ctx->n == n && ctx->last_status.grid_overflow + ctx->last_status.nbr_overflow + ctx->last_status.brick_overflow) {
+      // the contract graph uploaded the state and hit a table limit: replay on the plain path
+      if ((rc = pbf_step(ctx, nsteps)) != PBF_OK) return rc;
+      return pbf_download(ctx, px, py, pz, vx, vy, vz);
+    }
+  }
+  rc = upload_state(ctx, n, px, py, pz, vx, vy, vz, false);
   if (rc != PBF_OK) return rc;
   if ((rc = pbf_step(ctx, nsteps)) != PBF_OK) return rc;
   return pbf_download(ctx, px, py, pz, vx, vy, vz);

@@ -183,6 +183,12 @@ struct pbf_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_key = 0;
   int graph_kernels = 0;
+  // the cuda_step contract (pbf_step_host) as one graph: copies in, substep, copies out (pbf_capi.cu)
+  cudaGraphExec_t host_graph = nullptr;
+  const void* host_graph_ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int host_graph_kernels = 0;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // Frame snapshots (pbf_snapshot_begin / _wait): positions are unpacked into a device
   // staging copy on the compute stream and travel to library-owned pinned host buffers on a copy

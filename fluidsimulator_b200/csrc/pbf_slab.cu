@@ -1291,6 +1291,32 @@ int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi) {
   return PBF_OK;
 }
 
+// Bytes of PAYLOAD this slab sent to its neighbours during the last substep of the last batch
+// (messages travel at a fixed capacity with NCCL, so pbf_slab_stats' bytes_sent counts capacities;
+// the direct-store transport moves exactly the payload): per neighbour side, `hops` migration
+// messages of a header + (pos, pred) per migrant, the ghost build with a header + (pred, pos) of the
+// two boundary layers, and one float4 per boundary particle for every later refresh.
+int pbf_slab_payload(const pbf_ctx* ctx, uint64_t* bytes_last_substep) {
+  if (!ctx || !ctx->slab.enabled || !bytes_last_substep) return PBF_E_INVALID;
+  const SlabState& sl = ctx->slab;
+  *bytes_last_substep = 0;
+  if (!sl.counts_host) return PBF_OK;
+  const StepConsts& c = ctx->consts;
+  const int iters = ctx->params.solver_iterations;
+  const bool final_in_delta = !c.do_xsph && !c.do_vort;
+  const int refreshes = (iters > 0 ? (final_in_delta ? iters - 1 : iters) : 0) + ((iters > 0 && c.do_xsph && c.do_vort) ? 1 : 0);
+  uint64_t elems = 0;
+  for (int side = 0; side < 2; ++side) {
+    const bool has = side == 0 ? sl.rank > 0 : sl.rank + 1 < sl.nranks;
+    if (!has) continue;
+    const uint64_t moved = (uint64_t)std::max(0, sl.counts_host->n_send[side]);
+    const uint64_t layer = (uint64_t)std::max(0, sl.counts_host->b[side]);
+    elems += (uint64_t)sl.hops * (1 + 2 * moved) + (1 + 2 * layer) + (uint64_t)refreshes * layer;
+  }
+  *bytes_last_substep = elems * sizeof(float4);
+  return PBF_OK;
+}
+
 int pbf_slab_transport(const pbf_ctx* ctx) {
   if (!ctx || !ctx->slab.enabled || !ctx->slab.transport) return PBF_E_INVALID;
   if (const PeerTransport* pt = dynamic_cast<const PeerTransport*>(ctx->slab.transport))

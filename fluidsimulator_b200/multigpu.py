@@ -107,6 +107,49 @@ def make_slab(dist, local: int, params, planes, state, mode, stream_ptr=None) ->
     return sol
 
 
+def extra_run(dist, B, args, flags, scene: str, mode, rank, world, local, device, stream, barrier) -> dict:
+    """One more workload on the same ranks: K substeps after a warm-up, CUDA events, max over ranks;
+    with a parity witness when tests/golden/million.json holds a reference digest for the scene."""
+    import torch
+    params, planes, state = B.load_scene(scene, flags, args.iterations)
+    n = len(state[0])
+    sol = make_slab(dist, local, params, planes, state, mode, stream.cuda_stream)
+    parity, done = None, 0
+    gold = B.golden_digest(scene, args.flags, args.iterations, args.mode)
+    with torch.cuda.stream(stream):
+        if gold is not None:
+            step, expected = gold
+            sol.step(step)
+            done = step
+            gid_w, st_w = sol.slab_download()
+            full = gather_global(dist, gid_w, st_w, n, device)
+            if rank == 0:
+                got = B.combined16(full)
+                parity = {"step": step, "combined16": got, "expected": expected, "ok": got == expected, "slabs": world}
+            del full
+        warm = max(3, 3 - done)
+        sol.step(warm)      # first batches: plain launches (NCCL warm-up), then the captured graph
+        sol.step(warm)
+        steps = min(args.steps, 10)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        sol.step(steps)
+        ev1.record(stream)
+        barrier()
+        ms_t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        owned_t = torch.zeros(world, dtype=torch.int64, device=device)
+        owned_t[rank] = sol.owned()
+        dist.all_reduce(owned_t)
+    ms = float(ms_t.item())
+    out = {"value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps, "particles": n, "scene": scene,
+           "substeps": [done + 2 * warm, done + 2 * warm + steps], "transport": sol.transport(),
+           "owned_per_rank": [int(x) for x in owned_t.tolist()], "parity": parity}
+    sol.close()
+    return out
+
+
 def bench(args, flags, rank: int, world: int, local: int):
     """bench.py's N > 1 arm: strong scaling of one scene over `world` slabs (or --weak)."""
     import torch
@@ -162,6 +205,8 @@ def bench(args, flags, rank: int, world: int, local: int):
         launches = sol.launch_count() - launches0
         stats1 = sol.slab_stats()
         owned = sol.owned()
+        payload = sol.payload_bytes()
+        transport = sol.transport()
 
         # per-stage split of this rank (profiling mode: CUDA events around every stage)
         sol.profile_enable(True)
@@ -188,6 +233,18 @@ def bench(args, flags, rank: int, world: int, local: int):
         e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
 
+    # SURVEY §8e's larger workloads, device-timed the same way (extra keys, not the headline): the
+    # 16 M block on the same N slabs (strong scaling against extra.block_16m of the 1-GPU line) and
+    # 2 M particles per GPU (weak scaling)
+    extras = {}
+    if not args.no_extras and not args.weak:
+        sol.close()
+        for key, name in (("block_16m", "block_16m"), (f"weak_2m_per_gpu", f"weak_{world}")):
+            try:
+                extras[key] = extra_run(dist, B, args, flags, name, mode, rank, world, local, device, stream, barrier)
+            except Exception as e:  # an extra must never take the headline down
+                extras[key] = {"error": str(e)[:200]}
+
     # every rank's per-stage split (interior slabs carry two ghost sides, edge slabs one)
     my_stages = {k: v["ms"] / psteps for k, v in prof.items() if v["launches"]}
     all_stages = [None] * world
@@ -200,7 +257,6 @@ def bench(args, flags, rank: int, world: int, local: int):
     if rank != 0:
         return
     value = n * args.steps / (ms * 1e-3)
-    transport = sol.transport()
     peak, peak_src = B.measured_peaks()
     stages = {k: {"ms_per_step": v["ms"] / psteps, "launches_per_step": v["launches"] / psteps}
               for k, v in prof.items() if v["launches"]}
@@ -227,7 +283,7 @@ def bench(args, flags, rank: int, world: int, local: int):
                    "transport": transport,
                    "owned_per_rank": [int(x) for x in owned_t.tolist()],
                    "l2": "per-slab working set (neighbour list + particle arrays) re-streamed every substep; no explicit flush"},
-        "parity": parity,
+        "parity": parity, "extra": extras,
         "roofline": roofline, "cpu_baseline": None,
         "e2e": {"value": n * e2e_steps / float(e2e_t.item()), "unit": "particle-substeps/s",
                 "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
@@ -235,7 +291,8 @@ def bench(args, flags, rank: int, world: int, local: int):
         "gpu_launches": int(tot_launch.item()), "clocks": clocks, "stages": stages,
         "stages_per_rank_ms": [{k: round(v, 4) for k, v in st.items()} for st in all_stages],
         "exchange": {"per_substep": (stats1["exchanges"] - stats0["exchanges"]) / args.steps,
-                     "bytes_per_substep_rank0": (stats1["bytes_sent"] - stats0["bytes_sent"]) / args.steps,
+                     "payload_bytes_per_substep_rank0": payload,
+                     "capacity_bytes_per_substep_rank0": (stats1["bytes_sent"] - stats0["bytes_sent"]) / args.steps,
                      "ghosts_rank0": stats1["ghosts"], "hops": stats1["hops"]},
     }
     print(json.dumps(line), flush=True)

@@ -284,6 +284,9 @@ int pbf_slab_set_rebalance(pbf_ctx* ctx, float threshold);
 uint64_t pbf_slab_rebalance_count(const pbf_ctx* ctx);
 int pbf_slab_download(pbf_ctx* ctx, int64_t* global_id, float* px, float* py,
                       float* pz, float* vx, float* vy, float* vz);
+/* Payload bytes this slab sent during the last substep of the last batch (pbf_slab_stats counts
+ * message capacities, which is what NCCL messages move; peer stores move the payload only). */
+int pbf_slab_payload(const pbf_ctx* ctx, uint64_t* bytes_last_substep);
 /* Which data plane the last pbf_step batch of this slab used for its halo exchanges. */
 #define PBF_TRANSPORT_LOCAL_COPIES 1  /* one process: cudaMemcpyPeerAsync + events */
 #define PBF_TRANSPORT_NCCL_MESSAGES 2 /* ncclSend / ncclRecv between x-neighbours */

@@ -92,6 +92,42 @@ def test_step_host_contract(built):
         assert H.bit_equal(a, b)
 
 
+@pytest.mark.parametrize("flags", [H.STABLE_FLAGS, H.ALL_FLAGS, H.NO_FLAGS], ids=["stable", "all", "none"])
+def test_step_host_contract_pinned_graph(built, flags):
+    """The same contract on PAGE-LOCKED host arrays runs as one CUDA graph (copies in, substep, copies
+    out, the position download overlapped with the tail passes): bit-identical, including across a
+    table overflow inside the graph (K grows -> plain replay) and a change of host arrays."""
+    sol, orc, params = H.make_pair(scenes.SCENES["fluid_large"], flags, debug=False)
+
+    def pinned(arrays):
+        out = [a.copy() for a in arrays]
+        for a in out:
+            sol.host_register(a)
+        return out
+
+    import ctypes as C
+    sol.lib.pbf_debug_set_capacity.restype = C.c_int
+    sol.lib.pbf_debug_set_capacity.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    assert sol.lib.pbf_debug_set_capacity(sol.ctx, 8, 1 << 16) == 0   # the first substep overflows the neighbour table
+    st = pinned(orc.get_state())
+    for step in range(4):
+        sol.step_host(st, 1)
+        orc.step(1)
+        for a, b in zip(st, orc.get_state()):
+            assert H.bit_equal(a, b), f"step {step}"
+    st2 = pinned(st)   # other arrays: re-capture
+    for step in range(2):
+        sol.step_host(st2, 1)
+        orc.step(1)
+        for a, b in zip(st2, orc.get_state()):
+            assert H.bit_equal(a, b), f"second arrays, step {step}"
+    assert np.float32(sol.time) == np.float32(orc.time)
+    # and the device-resident state is the same thing
+    assert H.compare_state_bits(sol, orc) == []
+    for a in st + st2:
+        sol.host_unregister(a)
+
+
 def test_snapshot_is_the_state_of_its_moment(built):
     """pbf_snapshot_begin / _wait (asynchronous frame output): the positions a snapshot returns are
     those of the substep it was begun after, whatever ran in between; two slots are independent."""
