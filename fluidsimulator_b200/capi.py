@@ -137,9 +137,11 @@ ABI = {
     "pbf_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pbf_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_set_brick": (C.c_int, [C.c_void_p, C.c_int]),
+    "pbf_strict_exact": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p)]),
     "pbf_brick_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "pbf_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [_f32p] * 6),
     "pbf_download": (C.c_int, [C.c_void_p] + [_f32p] * 6),
+    "pbf_batches_retried": (C.c_uint64, [C.c_void_p]),
     "pbf_snapshot_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "pbf_snapshot_wait": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(_f32p)] * 3 + [C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
     "pbf_step": (C.c_int, [C.c_void_p, C.c_int]),
@@ -278,6 +280,14 @@ class Solver:
     def set_graph(self, enabled: bool):
         self._check(self.lib.pbf_set_graph(self.ctx, int(enabled)))
 
+    def strict_exact(self):
+        """(True, None) when STRICT results are bit-identical to the reference for the current
+        parameters, else (False, reason)."""
+        why = C.c_char_p()
+        rc = self.lib.pbf_strict_exact(self.ctx, C.byref(why))
+        self._check(min(rc, 0))
+        return rc == 1, (why.value.decode() if why.value else None)
+
     def set_brick(self, mode: int):
         """PBF_BRICK_OFF (global-gather kernels, default), PBF_BRICK_PERSISTENT or PBF_BRICK_PER_CTA
         (shared-memory staged bricks).  Same results bit for bit."""
@@ -303,6 +313,10 @@ class Solver:
         out = [np.empty(n, dtype=np.float32) for _ in range(6)]
         self._check(self.lib.pbf_download(self.ctx, *[fptr(a) for a in out]))
         return out
+
+    def batches_retried(self) -> int:
+        """Batches replayed so far because a device table had to grow (transparent, but not free)."""
+        return int(self.lib.pbf_batches_retried(self.ctx))
 
     def host_register(self, arr: np.ndarray):
         """Page-lock a host array in place (pbf_host_register): copies to and from it then run at

@@ -162,17 +162,34 @@ bool cuda_device_available(int* count, const char** error) {  // cuda_stub.cu:74
 
 namespace {
 
-// The caller's vectors live across calls (main.cpp allocates State once): page-lock them where
-// they are, and again if a vector was re-allocated.  Failure to register is not an error — the
-// copies then go through the driver's staging buffers, as they would for any pageable memory.
+// The caller's vectors live across calls (the reference's main.cpp allocates State once and never
+// resizes it, app/src/main.cpp:189-230): page-lock them where they are, so the six copies of the
+// contract run at PCIe speed and pbf_step_host can replay the whole call as one graph.  CUDA
+// requires page-locked memory to be unregistered BEFORE it is freed, which a library cannot
+// guarantee for memory it does not own: a caller that resizes or destroys State between calls must
+// set PBF_PIN_STATE=0 (copies then go through the driver's staging buffers, as for any pageable
+// memory).  A changed data() pointer is detected and never unregistered through the stale address
+// — the stale registration is dropped from the books, not touched.  Failure to register is not an
+// error either.
+bool pinning_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("PBF_PIN_STATE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 void pin_state(State& state) {
+  if (!pinning_enabled()) return;
   Backend& b = backend();
   std::vector<float>* arrays[6] = {&state.pos_x, &state.pos_y, &state.pos_z, &state.vel_x, &state.vel_y, &state.vel_z};
   for (int a = 0; a < 6; ++a) {
     void* ptr = arrays[a]->data();
     const std::size_t bytes = arrays[a]->size() * sizeof(float);
     if (ptr == b.pinned_ptr[a] && bytes == b.pinned_bytes[a]) continue;
-    if (b.pinned_ptr[a]) pbf_host_unregister(b.ctx, b.pinned_ptr[a]);
+    // same storage, other size: still ours to unregister.  Other storage: the old block has been
+    // freed by the vector — forget it (unregistering a freed range is undefined).
+    if (b.pinned_ptr[a] && b.pinned_ptr[a] == ptr) pbf_host_unregister(b.ctx, b.pinned_ptr[a]);
     b.pinned_ptr[a] = nullptr;
     b.pinned_bytes[a] = 0;
     if (bytes && pbf_host_register(b.ctx, ptr, bytes) == PBF_OK) {

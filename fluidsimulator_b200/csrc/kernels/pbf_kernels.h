@@ -171,9 +171,11 @@ int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s);
 // re-balancing support: this slab's owned count into the status block; x-cell range and per-layer
 // histogram of the owned particles (positions after the batch)
 int launch_slab_report(const SlabBuffers& sb, int rank, cudaStream_t s);
-int launch_slab_xrange(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int* out_min_max, cudaStream_t s);
-int launch_slab_xhist(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int x_min, int layers,
-                      unsigned long long* hist, cudaStream_t s);
+// (x-cells of pos + vel * lookahead: where the particles will be when the new cuts are in use)
+int launch_slab_xrange(const float4* pos_o, const float4* vel_o, const SlabBuffers& sb, const StepConsts& c, float lookahead,
+                       int* out_min_max, cudaStream_t s);
+int launch_slab_xhist(const float4* pos_o, const float4* vel_o, const SlabBuffers& sb, const StepConsts& c, float lookahead,
+                      int x_min, int layers, unsigned long long* hist, cudaStream_t s);
 // ghost velocities (pred - pos)/dt and m/rho, recomputed locally after the last pred refresh
 int launch_slab_ghost_vel(const float4* pred_final, const float4* pos_s, const float* rho, float4* vel, PosVel* pv,
                           const SlabBuffers& sb, const StepConsts& c, bool strict, cudaStream_t s);

@@ -40,13 +40,13 @@ __device__ __forceinline__ int slab_class(float x, float inv_h, int cut_lo, int 
 __global__ void __launch_bounds__(kThreads)
 k_slab_leave(const float4* __restrict__ pos_o, const float4* __restrict__ pred_o, const uint32_t* __restrict__ gid_o,
              SlabCounts* __restrict__ counts, uint32_t* __restrict__ holes, float4* __restrict__ send_l,
-             float4* __restrict__ send_r, const StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int mcap) {
+             float4* __restrict__ send_r, const StatusBlock* st, float inv_h, int mcap) {
   pdl_wait();
   if (batch_failed(st)) return;
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= counts->n_own) return;
   const float4 q = pred_o[i];
-  const int cls = slab_class(q.x, inv_h, cut_lo, cut_hi);
+  const int cls = slab_class(q.x, inv_h, counts->cut_lo, counts->cut_hi);
   if (cls == 0) return;
   const int k = atomicAdd(&counts->n_send[cls - 1], 1);
   if (k < mcap) {
@@ -63,9 +63,10 @@ k_slab_leave(const float4* __restrict__ pos_o, const float4* __restrict__ pred_o
 __global__ void __launch_bounds__(1024)
 k_slab_refill(float4* __restrict__ pos_o, float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o,
               SlabCounts* __restrict__ counts, uint32_t* __restrict__ holes, float4* send_l, float4* send_r,
-              StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int mcap) {
+              StatusBlock* st, float inv_h, int mcap) {
   pdl_wait();
   __shared__ int s_a, s_b;
+  const int cut_lo = counts->cut_lo, cut_hi = counts->cut_hi;
   if (batch_failed(st)) {
     if (threadIdx.x == 0) send_l[0] = send_r[0] = hdr_fail();
     return;
@@ -107,9 +108,10 @@ k_slab_refill(float4* __restrict__ pos_o, float4* __restrict__ pred_o, uint32_t*
 __global__ void __launch_bounds__(kThreads)
 k_slab_arrive(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pos_o,
               float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o, SlabCounts* __restrict__ counts,
-              StatusBlock* st, float inv_h, int cut_lo, int cut_hi, int cap, int mcap, int last_hop) {
+              StatusBlock* st, float inv_h, int cap, int mcap, int last_hop) {
   pdl_wait();
   if (batch_failed(st)) return;
+  const int cut_lo = counts->cut_lo, cut_hi = counts->cut_hi;
   if (hdr_failed(recv_l) || hdr_failed(recv_r)) {
     st->peer_failed = 1;
     return;
@@ -166,8 +168,9 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys
 // The two x-layers next to a cut are a prefix (left) / suffix (right) of the sorted owned slots.
 __global__ void k_slab_bounds(const uint32_t* __restrict__ keys, const GridDesc* __restrict__ desc,
                               SlabCounts* __restrict__ counts, StatusBlock* st, float4* send_l, float4* send_r,
-                              int cut_lo, int cut_hi, int gcap) {
+                              int gcap) {
   pdl_wait();
+  const int cut_lo = counts->cut_lo, cut_hi = counts->cut_hi;
   if (batch_failed(st)) {
     send_l[0] = send_r[0] = hdr_fail();
     return;
@@ -329,11 +332,14 @@ __global__ void k_slab_report(const SlabCounts* __restrict__ counts, StatusBlock
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_slab_xrange(const float4* __restrict__ pos_o, const SlabCounts* __restrict__ counts, float inv_h, int* out) {
+k_slab_xrange(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o, const SlabCounts* __restrict__ counts,
+              float inv_h, float lookahead, int* out) {
   pdl_wait();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   int lo = INT_MAX, hi = INT_MIN;
-  if (i < counts->n_own) lo = hi = cell_coord(pos_o[i].x, inv_h);
+  // where the particle will be `lookahead` seconds from now if it keeps its velocity: the cuts are
+  // planned for the middle of the batch they will serve, not for the moment of planning
+  if (i < counts->n_own) lo = hi = cell_coord(fmaf(vel_o[i].x, lookahead, pos_o[i].x), inv_h);
   lo = __reduce_min_sync(0xffffffffu, lo);
   hi = __reduce_max_sync(0xffffffffu, hi);
   if ((threadIdx.x & 31) == 0 && lo != INT_MAX) {
@@ -343,12 +349,12 @@ k_slab_xrange(const float4* __restrict__ pos_o, const SlabCounts* __restrict__ c
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_slab_xhist(const float4* __restrict__ pos_o, const SlabCounts* __restrict__ counts, float inv_h, int x_min,
-             int layers, unsigned long long* __restrict__ hist) {
+k_slab_xhist(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o, const SlabCounts* __restrict__ counts,
+             float inv_h, float lookahead, int x_min, int layers, unsigned long long* __restrict__ hist) {
   pdl_wait();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= counts->n_own) return;
-  const long long l = (long long)cell_coord(pos_o[i].x, inv_h) - x_min;
+  const long long l = (long long)cell_coord(fmaf(vel_o[i].x, lookahead, pos_o[i].x), inv_h) - x_min;
   if (l >= 0 && l < layers) atomicAdd(&hist[l], 1ull);
 }
 
@@ -359,24 +365,23 @@ inline int grid_for(int n) { return (n + kThreads - 1) / kThreads; }
 // ================================================================== launchers
 int launch_slab_split(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, cudaStream_t s) {
   PBF_LAUNCH(k_slab_leave, grid_for(sb.cap), kThreads, s, pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0],
-                                                    sb.send[1], sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, sb.mcap);
+                                                    sb.send[1], sb.status, c.inv_h, sb.mcap);
   PBF_LAUNCH(k_slab_refill, 1, 1024, s, pos_o, pred_o, sb.gid_o, sb.counts, sb.holes, sb.send[0], sb.send[1], sb.status,
-                                  c.inv_h, sb.cut_lo, sb.cut_hi, sb.mcap);
+                                  c.inv_h, sb.mcap);
   return 2;
 }
 
 int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, const StepConsts& c, bool last_hop,
                       cudaStream_t s) {
   PBF_LAUNCH(k_slab_arrive, grid_for(2 * sb.mcap), kThreads, s, sb.recv[0], sb.recv[1], pos_o, pred_o, sb.gid_o, sb.counts,
-                                                          sb.status, c.inv_h, sb.cut_lo, sb.cut_hi, sb.cap, sb.mcap,
+                                                          sb.status, c.inv_h, sb.cap, sb.mcap,
                                                           last_hop ? 1 : 0);
   return 1;
 }
 
 int launch_slab_ghost_pack(const uint32_t* keys_sorted, const float4* pred_s, const float4* pos_s,
                            const GridBuffers& g, const SlabBuffers& sb, cudaStream_t s) {
-  PBF_LAUNCH(k_slab_bounds, 1, 1, s, keys_sorted, g.desc, sb.counts, sb.status, sb.send[0], sb.send[1], sb.cut_lo,
-                               sb.cut_hi, sb.gcap);
+  PBF_LAUNCH(k_slab_bounds, 1, 1, s, keys_sorted, g.desc, sb.counts, sb.status, sb.send[0], sb.send[1], sb.gcap);
   PBF_LAUNCH(k_slab_ghost_pack, grid_for(2 * sb.gcap), kThreads, s, pred_s, pos_s, sb.counts, sb.send[0], sb.send[1],
                                                               sb.status, sb.gcap);
   return 2;
@@ -401,14 +406,15 @@ int launch_slab_report(const SlabBuffers& sb, int rank, cudaStream_t s) {
   return 1;
 }
 
-int launch_slab_xrange(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int* out_min_max, cudaStream_t s) {
-  PBF_LAUNCH(k_slab_xrange, grid_for(sb.cap), kThreads, s, pos_o, sb.counts, c.inv_h, out_min_max);
+int launch_slab_xrange(const float4* pos_o, const float4* vel_o, const SlabBuffers& sb, const StepConsts& c, float lookahead,
+                       int* out_min_max, cudaStream_t s) {
+  PBF_LAUNCH(k_slab_xrange, grid_for(sb.cap), kThreads, s, pos_o, vel_o, sb.counts, c.inv_h, lookahead, out_min_max);
   return 1;
 }
 
-int launch_slab_xhist(const float4* pos_o, const SlabBuffers& sb, const StepConsts& c, int x_min, int layers,
-                      unsigned long long* hist, cudaStream_t s) {
-  PBF_LAUNCH(k_slab_xhist, grid_for(sb.cap), kThreads, s, pos_o, sb.counts, c.inv_h, x_min, layers, hist);
+int launch_slab_xhist(const float4* pos_o, const float4* vel_o, const SlabBuffers& sb, const StepConsts& c, float lookahead,
+                      int x_min, int layers, unsigned long long* hist, cudaStream_t s) {
+  PBF_LAUNCH(k_slab_xhist, grid_for(sb.cap), kThreads, s, pos_o, vel_o, sb.counts, c.inv_h, lookahead, x_min, layers, hist);
   return 1;
 }
 

@@ -162,6 +162,21 @@ int ensure_tables(pbf_ctx* ctx) {
   const size_t need = ((slots + 31) / 32) * (size_t)ctx->K * 32u;
   if (ctx->nbr_idx.n < need) {
     invalidate_graph(ctx);
+    // The list is an ELL table: K = the largest neighbour count of any particle.  In the reference's
+    // own divergence (vorticity on, SURVEY §0: ~10 000 particles in one cell) K reaches five digits;
+    // say so instead of failing inside cudaMalloc.
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t have = ctx->nbr_idx.n * sizeof(uint32_t);
+      if (need * sizeof(uint32_t) > free_b + have) {
+        char buf[320];
+        std::snprintf(buf, sizeof(buf),
+                      "pbf_step: the neighbour table needs %.1f GB (K = %d neighbours for %zu slots) but only %.1f GB of "
+                      "device memory are free; the scene has collapsed into a few cells (state restored to the start of the batch)",
+                      (double)need * 4e-9, ctx->K, slots, (double)(free_b + have) * 1e-9);
+        return fail(ctx, PBF_E_CAPACITY, buf);
+      }
+    }
     PBF_CUDA(ctx, ctx->nbr_idx.reserve(need));
     // rows are only filled up to each particle's count; the debug surface copies whole rows
     PBF_CUDA(ctx, cudaMemsetAsync(ctx->nbr_idx.p, 0, need * sizeof(uint32_t), ctx->stream));
@@ -541,6 +556,29 @@ int pbf_set_params(pbf_ctx* ctx, const pbf_params* p) {
   ctx->consts = make_consts(ctx->params, (int)ctx->planes_host.size());
   invalidate_graph(ctx);
   return PBF_OK;
+}
+
+// 1 when STRICT results are bit-identical to the reference CPU path for the current parameters,
+// 0 (with a reason) for the configurations where they are only close:
+//   * s_corr with an exponent outside {2, 3, 4}: the reference calls std::pow (core.cpp:59-71), the
+//     device powf — not the same bits;
+//   * solver_iterations == 0 with XSPH or vorticity on: the reference still runs those passes on
+//     whatever rho its scratch arrays hold from an earlier call; this backend only commits.
+// (NaN inputs are a third case: the max(x, 0) clamps of the kernels return 0 where the reference's
+// branches propagate NaN; no parameter check can see that.)
+int pbf_strict_exact(const pbf_ctx* ctx, const char** why) {
+  if (why) *why = nullptr;
+  if (!ctx) return PBF_E_INVALID;
+  const pbf_params& p = ctx->params;
+  if (p.enable_scorr && (p.scorr_n < 2 || p.scorr_n > 4)) {
+    if (why) *why = "s_corr exponent outside {2,3,4}: device powf vs host std::pow";
+    return 0;
+  }
+  if (p.solver_iterations == 0 && (p.enable_xsph || p.enable_vorticity)) {
+    if (why) *why = "solver_iterations == 0 with XSPH / vorticity: the reference runs them on stale rho, this backend only commits";
+    return 0;
+  }
+  return 1;
 }
 
 int pbf_set_planes(pbf_ctx* ctx, int count, const float* nx, const float* ny, const float* nz, const float* d) {
@@ -928,6 +966,7 @@ int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float
   return pbf_download(ctx, px, py, pz, vx, vy, vz);
 }
 
+uint64_t pbf_batches_retried(const pbf_ctx* ctx) { return ctx ? ctx->batches_retried : 0; }
 size_t pbf_count(const pbf_ctx* ctx) { return ctx ? ctx->n : 0; }
 float pbf_time(const pbf_ctx* ctx) { return ctx ? ctx->time : 0.0f; }
 int pbf_set_time(pbf_ctx* ctx, float t) {

@@ -91,7 +91,7 @@ struct SlabState {
   uint64_t bytes_sent = 0;
   uint64_t graph_exchanges = 0, graph_bytes = 0;  // per replay of the captured substep
   bool warm = false;                       // a batch has completed since the communicator was joined
-  float rebalance_threshold = 1.3f;        // re-plan the cuts when max / mean owned exceeds it (0 = never)
+  float rebalance_threshold = 1.1f;         // re-plan the cuts when max / mean owned exceeds it (0 = never)
   double planned_ratio = 1.0;              // max / mean owned the last automatic plan produced by itself
   uint64_t rebalances = 0;
   DevBuf<unsigned long long> hist_dev;     // x-layer histogram / staging of host all-reduces

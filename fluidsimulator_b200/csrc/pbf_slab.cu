@@ -787,6 +787,8 @@ int set_device_count(pbf_ctx* ctx, int n_own) {
   std::memset(sl.counts_host, 0, sizeof(SlabCounts));
   sl.counts_host->n_own = n_own;
   sl.counts_host->n_tot = n_own;
+  sl.counts_host->cut_lo = sl.cut_lo;  // read by the migration / ghost kernels from device memory
+  sl.counts_host->cut_hi = sl.cut_hi;
   PBF_CUDA(ctx, cudaMemcpyAsync(sl.counts.p, sl.counts_host, sizeof(SlabCounts), cudaMemcpyHostToDevice, ctx->stream));
   return PBF_OK;
 }
@@ -794,6 +796,16 @@ int set_device_count(pbf_ctx* ctx, int n_own) {
 }  // namespace
 
 namespace {
+
+// Substeps per slab batch (see slab_step): PBF_SLAB_CHUNK, default 25.
+int slab_chunk() {
+  static const int chunk = [] {
+    const char* e = std::getenv("PBF_SLAB_CHUNK");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 25;
+  }();
+  return chunk;
+}
 
 // Automatic re-balancing.  Every rank sees every slab's owned count in the max-reduced status
 // block; when the largest slab exceeds the mean by the threshold, all ranks together build the
@@ -819,7 +831,10 @@ int maybe_rebalance(pbf_ctx* ctx, const StatusBlock& st) {
   int* range_dev = reinterpret_cast<int*>(sl.hist_dev.p);
   const int init[2] = {INT_MAX, INT_MIN};
   PBF_CUDA(ctx, cudaMemcpyAsync(range_dev, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->launch_count += (uint64_t)launch_slab_xrange(ctx->pos_o.p, sb, ctx->consts, range_dev, ctx->stream);
+  // plan for the later part of the next batch (imbalance grows along it): positions advanced by 3/4
+  // of a batch at constant velocity
+  const float lookahead = 0.75f * (float)slab_chunk() * ctx->params.dt;
+  ctx->launch_count += (uint64_t)launch_slab_xrange(ctx->pos_o.p, ctx->vel_o.p, sb, ctx->consts, lookahead, range_dev, ctx->stream);
   int range[2];
   PBF_CUDA(ctx, cudaMemcpyAsync(range, range_dev, sizeof(range), cudaMemcpyDeviceToHost, ctx->stream));
   PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -832,8 +847,8 @@ int maybe_rebalance(pbf_ctx* ctx, const StatusBlock& st) {
   // histogram of the whole scene
   PBF_CUDA(ctx, sl.hist_dev.reserve((size_t)layers));
   PBF_CUDA(ctx, cudaMemsetAsync(sl.hist_dev.p, 0, (size_t)layers * sizeof(unsigned long long), ctx->stream));
-  ctx->launch_count += (uint64_t)launch_slab_xhist(ctx->pos_o.p, sb, ctx->consts, (int)x_min, (int)layers, sl.hist_dev.p,
-                                                   ctx->stream);
+  ctx->launch_count += (uint64_t)launch_slab_xhist(ctx->pos_o.p, ctx->vel_o.p, sb, ctx->consts, lookahead, (int)x_min,
+                                                   (int)layers, sl.hist_dev.p, ctx->stream);
   std::vector<long long> hist((size_t)layers);
   PBF_CUDA(ctx, cudaMemcpyAsync(hist.data(), sl.hist_dev.p, (size_t)layers * sizeof(long long), cudaMemcpyDeviceToHost,
                                 ctx->stream));
@@ -853,11 +868,46 @@ int maybe_rebalance(pbf_ctx* ctx, const StatusBlock& st) {
     planned_max = std::max(planned_max, own);
   }
   sl.planned_ratio = std::max(1.0, (double)planned_max * sl.nranks / (double)total);
+  if (std::getenv("PBF_SLAB_DEBUG") && sl.rank == 0) {
+    std::fprintf(stderr, "[replan] x layers %lld..%lld total %llu largest %llu planned_max %llu cuts:", x_min, x_max, total, largest,
+                 planned_max);
+    for (int r = 1; r < sl.nranks; ++r) std::fprintf(stderr, " %d", cuts[(size_t)r]);
+    std::fprintf(stderr, " | own_by_rank:");
+    for (int r = 0; r < sl.nranks; ++r) std::fprintf(stderr, " %u", st.own_by_rank[r]);
+    std::fprintf(stderr, " | hist:");
+    for (size_t l = 0; l < h.size(); ++l) std::fprintf(stderr, " %zu", h[l]);
+    std::fprintf(stderr, "\n");
+  }
   sl.rebalances++;  // the decision is global: every rank counts it, whether or not its own cuts move
+  // The particles between an old and a new cut change owner during the next substep, whole cell
+  // layers at once: size the migration messages for that now (identically on every rank: the largest
+  // move of any cut), instead of letting the next batch overflow, grow and replay.
+  {
+    auto layer_sum = [&](long long a, long long b) {  // particles in the layers [a, b) of the histogram
+      unsigned long long sum = 0;
+      for (long long l = std::max(0LL, a); l < std::min(layers, b); ++l) sum += h[(size_t)l];
+      return sum;
+    };
+    unsigned long long moved = 0;
+    if (sl.rank > 0 && sl.cut_lo != INT_MIN) {
+      const long long o = (long long)sl.cut_lo - x_min, n = (long long)cuts[(size_t)sl.rank] - x_min;
+      moved = std::max(moved, layer_sum(std::min(o, n), std::max(o, n)));
+    }
+    if (sl.rank + 1 < sl.nranks && sl.cut_hi != INT_MAX) {
+      const long long o = (long long)sl.cut_hi - x_min, n = (long long)cuts[(size_t)sl.rank + 1] - x_min;
+      moved = std::max(moved, layer_sum(std::min(o, n), std::max(o, n)));
+    }
+    long long m = (long long)moved;
+    if ((rc = sl.transport->allreduce_host(ctx, &m, 1, 0)) != PBF_OK) return rc;
+    const long long want = m + m / 4 + 1024;
+    if (want > (long long)sl.mcap && want < (1LL << 30)) {
+      sl.mcap = (int)want;
+      invalidate_graph(ctx);  // message capacities are kernel parameters and buffer sizes
+    }
+  }
   if (cuts[(size_t)sl.rank] == sl.cut_lo && cuts[(size_t)sl.rank + 1] == sl.cut_hi) return PBF_OK;
   sl.cut_lo = cuts[(size_t)sl.rank];
-  sl.cut_hi = cuts[(size_t)sl.rank + 1];
-  invalidate_graph(ctx);  // the cuts are kernel parameters of the captured substep
+  sl.cut_hi = cuts[(size_t)sl.rank + 1];  // device data (SlabCounts): the captured substep graph stays valid
   return PBF_OK;
 }
 
@@ -885,7 +935,27 @@ void slab_release(pbf_ctx* ctx) {
 // pbf_step of a slab context.  Every rank of the communicator (or every thread of the group)
 // calls it with the same nsteps; the grow-and-replay decision is taken on max-reduced status
 // words, so all ranks replay together.
+static int slab_batch(pbf_ctx* ctx, int nsteps);
+
+// A long pbf_step call is cut into batches of at most `chunk` substeps (PBF_SLAB_CHUNK, default 25):
+// table capacities and the cuts are only re-decided BETWEEN batches, and a fluid that is spreading
+// (fluid_million after its floor impact: the end slabs go from 130 k to 300 k particles within 100
+// substeps) must not run that long on stale cuts — nor replay 100 substeps because a message buffer
+// overflowed in the 90th.  Every rank makes the same cuts of the same nsteps, so the call stays
+// collective.  Cost: one status reduction and host round trip per batch (~0.1 ms per 25 substeps).
+// On failure the state is that of the last completed batch (time advanced accordingly).
 int slab_step(pbf_ctx* ctx, int nsteps) {
+  const int chunk = slab_chunk();
+  for (int done = 0; done < nsteps;) {
+    const int k = std::min(chunk, nsteps - done);
+    const int rc = slab_batch(ctx, k);
+    if (rc != PBF_OK) return rc;
+    done += k;
+  }
+  return PBF_OK;
+}
+
+static int slab_batch(pbf_ctx* ctx, int nsteps) {
   SlabState& sl = ctx->slab;
   if (!sl.transport) return fail(ctx, PBF_E_COMM, "pbf_step: slab context without a communicator");
   int rc;
@@ -1017,20 +1087,24 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       ctx->n = (size_t)sl.counts_host->n_own;
       for (int s = 0; s < nsteps; ++s) ctx->time += ctx->params.dt;
       sl.warm = true;
+      // Messages are sent at full capacity (their size is not known to the host), so capacities
+      // follow the observed maxima down as well as up.  The maxima are max-reduced over the slabs:
+      // every rank takes the same decision.  Shrinking re-allocates and re-captures the substep
+      // graph (~1 ms) and, with peer windows, re-opens the IPC handles (~10 ms), so it needs a factor
+      // of two, and growth (below) overshoots by half: a spreading fluid must not
+      // re-capture every batch.  Before the re-plan: that one sizes the migration messages for the
+      // layers it moves.
+      // (Migration messages only grow: with direct peer stores their capacity costs memory, not
+      // bandwidth, and a re-plan needs them large again a few batches later.)
+      const int want_g = (int)(st.max_ghost + st.max_ghost / 2 + 1024);
+      if (want_g < sl.gcap / 2) {
+        sl.gcap = want_g;
+        sl.tot_cap = ctx->cap + 2 * (size_t)sl.gcap;
+        invalidate_graph(ctx);
+      }
       if ((rc = maybe_rebalance(ctx, st)) != PBF_OK) {  // the batch itself is complete: keep its result
         sl.transport->abort();
         return rc;
-      }
-      // Messages are sent at full capacity (their size is not known to the host), so capacities
-      // follow the observed maxima down as well as up.  The maxima are max-reduced over the slabs:
-      // every rank takes the same decision.
-      const int want_g = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
-      const int want_m = (int)(st.max_send + st.max_send / 2 + 1024);
-      if (want_g < sl.gcap - sl.gcap / 4 || want_m < sl.mcap / 2) {
-        if (want_g < sl.gcap - sl.gcap / 4) sl.gcap = want_g;
-        if (want_m < sl.mcap / 2) sl.mcap = want_m;
-        sl.tot_cap = ctx->cap + 2 * (size_t)sl.gcap;
-        invalidate_graph(ctx);
       }
       return PBF_OK;
     }
@@ -1047,8 +1121,10 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       ctx->cell_cap = cap;
     }
     if (st.nbr_overflow) ctx->K = (int)((st.max_neighbors + st.max_neighbors / 2 + 16 + 7u) & ~7u);
-    if (st.mig_overflow) sl.mcap = (int)(st.max_send + st.max_send / 2 + 1024);
-    if (st.ghost_overflow) sl.gcap = (int)(st.max_ghost + st.max_ghost / 4 + 1024);
+    // the batch stopped at the first overflowing substep: the maxima are lower bounds of what the
+    // rest of it needs, so overshoot
+    if (st.mig_overflow) sl.mcap = std::max(8192, (int)(2 * st.max_send + 1024));
+    if (st.ghost_overflow) sl.gcap = (int)(st.max_ghost + st.max_ghost / 2 + 1024);
     // far_migrant only counts when nothing else went wrong (a slab that stopped early leaves its
     // neighbours with incomplete data, which can look like a stray particle)
     const bool other = (st.grid_overflow | st.nbr_overflow | st.mig_overflow | st.ghost_overflow | st.own_overflow) != 0;
@@ -1058,7 +1134,7 @@ int slab_step(pbf_ctx* ctx, int nsteps) {
       sl.hops++;
     }
     size_t want = ctx->cap;
-    if (st.own_overflow) want = std::max<size_t>(want, (size_t)st.max_own + st.max_own / 4 + 1024);
+    if (st.own_overflow) want = std::max<size_t>(want, (size_t)st.max_own + st.max_own / 2 + 1024);
     if (st.own_overflow || st.ghost_overflow) {
       // tot_cap = cap + 2 * gcap must cover max_own (owned + ghosts)
       ctx->cap = 0;  // force the resize below
@@ -1102,7 +1178,7 @@ int slab_take(pbf_ctx* ctx, size_t n_global, const float* px, const float* py, c
   const size_t n_max = *std::max_element(per_rank.begin(), per_rank.end());
   const size_t cap = n_max + n_max / 4 + 4096;
   if (sl.gcap == 0) sl.gcap = (int)std::max<size_t>(16384, cap / 2);
-  if (sl.mcap == 0) sl.mcap = (int)std::max<size_t>(8192, cap / 16);
+  if (sl.mcap == 0) sl.mcap = (int)std::max<size_t>(8192, cap / 4);  // a re-plan moves whole cell layers at once
   int rc = ensure_particles(ctx, cap, 0);
   if (rc != PBF_OK) return rc;
   if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;
@@ -1271,8 +1347,7 @@ int pbf_slab_set_cuts(pbf_ctx* ctx, int32_t lo, int32_t hi) {
       (long long)hi - (long long)lo < 2)
     return fail(ctx, PBF_E_INVALID, "pbf_slab_set_cuts: cuts must tile the x axis with >= 2 cell layers per slab");
   ctx->slab.cut_lo = lo;
-  ctx->slab.cut_hi = hi;
-  invalidate_graph(ctx);  // the cuts are kernel parameters of the captured substep
+  ctx->slab.cut_hi = hi;  // uploaded with the counts at the start of the next batch
   return PBF_OK;
 }
 

@@ -99,6 +99,12 @@ int pbf_set_params(pbf_ctx* ctx, const pbf_params* params);
 int pbf_set_planes(pbf_ctx* ctx, int count, const float* nx, const float* ny,
                    const float* nz, const float* d);
 int pbf_set_mode(pbf_ctx* ctx, int mode);
+/* Is the current parameter set inside the domain where PBF_MODE_STRICT is bit-identical to the
+ * reference CPU path?  1 = yes; 0 = no, *why (may be NULL) names the reason: an s_corr exponent
+ * outside {2,3,4} (reference: std::pow, core.cpp:59-71) or solver_iterations == 0 with XSPH /
+ * vorticity enabled (reference: those passes run on stale scratch, core.cpp:423-571).  Every
+ * shipped scene and every CLI flag combination of the reference is inside the domain. */
+int pbf_strict_exact(const pbf_ctx* ctx, const char** why);
 /* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) so that the
  * caller's CUDA events bracket the work.  NULL = the context's own stream. */
 int pbf_set_stream(pbf_ctx* ctx, void* cuda_stream);
@@ -122,6 +128,11 @@ int pbf_set_brick(pbf_ctx* ctx, int mode);
 /* Returns 1 if the last pbf_step batch ran on the brick path, 0 if not; optional outputs: batches
  * replayed on the global-gather family so far, largest tile (records) of the last batch. */
 int pbf_brick_status(const pbf_ctx* ctx, uint64_t* fallbacks, uint32_t* max_tile);
+
+/* Batches that were replayed so far because a device table (cell table, neighbour table, slab
+ * message or particle capacity) had to grow or a peer timed out.  Replays are transparent — results
+ * never depend on them — but they cost time: a benchmark reports this count for its timed region. */
+uint64_t pbf_batches_retried(const pbf_ctx* ctx);
 
 /* Asynchronous frame output (device-resident stepping; replaces the blocking read of positions for
  * the VTK writer at reference app/src/main.cpp:259-273).  pbf_snapshot_begin enqueues, after the
@@ -278,7 +289,7 @@ int pbf_slab_cuts(const pbf_ctx* ctx, int32_t* lo, int32_t* hi);
  * grows on demand), so results do not depend on when or how the cuts move. */
 int pbf_slab_set_cuts(pbf_ctx* ctx, int32_t lo, int32_t hi);
 /* Automatic re-balancing: at the end of a pbf_step batch, when the largest slab owns more than
- * `threshold` times the mean (default 1.3; 0 = never), all ranks re-plan equal-count cuts on the
+ * `threshold` times the mean (default 1.1; 0 = never), all ranks re-plan equal-count cuts on the
  * x-layer histogram of the whole scene.  Collective setting: the same value on every rank. */
 int pbf_slab_set_rebalance(pbf_ctx* ctx, float threshold);
 uint64_t pbf_slab_rebalance_count(const pbf_ctx* ctx);

@@ -157,6 +157,25 @@ def test_snapshot_is_the_state_of_its_moment(built):
     sol.snapshot_wait(0)
 
 
+def test_strict_exact_domain_is_reported(built):
+    """pbf_strict_exact names the two parameter sets where STRICT is not bit-pinned."""
+    sol, orc, params = H.make_pair(SMALL, H.ALL_FLAGS, debug=False)
+    assert sol.strict_exact() == (True, None)
+    p = params.copy()
+    p.scorr_n = 5
+    sol.set_params(p)
+    ok, why = sol.strict_exact()
+    assert not ok and "pow" in why
+    p = params.copy()
+    p.solver_iterations = 0
+    sol.set_params(p)
+    ok, why = sol.strict_exact()
+    assert not ok and "solver_iterations" in why
+    p.enable_xsph = p.enable_vorticity = 0
+    sol.set_params(p)
+    assert sol.strict_exact() == (True, None)
+
+
 def test_empty_state_advances_time(built):
     from fluidsimulator_b200.capi import Solver
     params, planes, st = scenes.load_scene(SMALL)
