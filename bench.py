@@ -330,11 +330,12 @@ def run_ours(args, flags):
         sol.step(args.warmup)
         torch.cuda.synchronize()
         sampler = ClockSampler(local)
-        launches0 = sol.launch_count()
+        launches0, retried0 = sol.launch_count(), sol.batches_retried()
         sampler.start()
         ms = timed_steps(sol, stream, args.steps)   # K substeps, device resident, one graph replay per substep
         clocks = sampler.stop()
         launches = sol.launch_count() - launches0
+        retried = sol.batches_retried() - retried0
         nbr_total = sol.debug_sizes()[1]
         brick = sol.brick_status()
 
@@ -406,7 +407,8 @@ def run_ours(args, flags):
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": n * e2e_steps / e2e_s, "unit": "particle-substeps/s", "h2d_bytes_per_step": 24 * n,
                 "d2h_bytes_per_step": 24 * n, "steps": e2e_steps, "call": "pbf_step_host (cuda_step contract)"},
-        "gpu_launches": launches, "clocks": clocks, "stages": stages, "ms_per_step_profiled": ms_prof / args.steps,
+        "gpu_launches": launches, "batches_replayed_in_timed_region": retried, "clocks": clocks, "stages": stages,
+        "ms_per_step_profiled": ms_prof / args.steps,
         "extra": extras,
     }
     print(json.dumps(line), flush=True)

@@ -1176,9 +1176,14 @@ int slab_take(pbf_ctx* ctx, size_t n_global, const float* px, const float* py, c
   // Message capacities are part of the wire format (fixed-size messages, payload offsets), so
   // they are derived from the LARGEST slab: every rank computes the same numbers.
   const size_t n_max = *std::max_element(per_rank.begin(), per_rank.end());
-  const size_t cap = n_max + n_max / 4 + 4096;
+  // Generous on purpose: growing a capacity later means re-allocating every per-particle array,
+  // re-opening the peer windows and re-capturing the substep graph (tens of ms, measured on 8 GPUs
+  // when fluid_million's splash drove the end slabs from 130 k to 180 k owned particles), while a
+  // slot costs ~700 bytes of a 180 GB device.  A re-plan moves whole cell layers at once, and with
+  // direct peer stores a message's capacity costs memory, not bandwidth.
+  const size_t cap = 2 * n_max + 4096;
   if (sl.gcap == 0) sl.gcap = (int)std::max<size_t>(16384, cap / 2);
-  if (sl.mcap == 0) sl.mcap = (int)std::max<size_t>(8192, cap / 4);  // a re-plan moves whole cell layers at once
+  if (sl.mcap == 0) sl.mcap = (int)std::max<size_t>(8192, cap / 2);
   int rc = ensure_particles(ctx, cap, 0);
   if (rc != PBF_OK) return rc;
   if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return rc;

@@ -190,7 +190,7 @@ def bench(args, flags, rank: int, world: int, local: int):
         sol.step(args.warmup)
         barrier()
         sampler = B.ClockSampler(local)
-        launches0 = sol.launch_count()
+        launches0, retried0, replans0 = sol.launch_count(), sol.batches_retried(), sol.rebalance_count()
         stats0 = sol.slab_stats()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler.start()
@@ -203,6 +203,7 @@ def bench(args, flags, rank: int, world: int, local: int):
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         ms = float(ms_t.item())
         launches = sol.launch_count() - launches0
+        retried, replans = sol.batches_retried() - retried0, sol.rebalance_count() - replans0
         stats1 = sol.slab_stats()
         owned = sol.owned()
         payload = sol.payload_bytes()
@@ -288,7 +289,8 @@ def bench(args, flags, rank: int, world: int, local: int):
         "e2e": {"value": n * e2e_steps / float(e2e_t.item()), "unit": "particle-substeps/s",
                 "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
                 "call": "per rank: pbf_slab_upload_owned + pbf_step(1) + pbf_slab_download"},
-        "gpu_launches": int(tot_launch.item()), "clocks": clocks, "stages": stages,
+        "gpu_launches": int(tot_launch.item()), "batches_replayed_in_timed_region": retried,
+        "cut_replans_in_timed_region": replans, "clocks": clocks, "stages": stages,
         "stages_per_rank_ms": [{k: round(v, 4) for k, v in st.items()} for st in all_stages],
         "exchange": {"per_substep": (stats1["exchanges"] - stats0["exchanges"]) / args.steps,
                      "payload_bytes_per_substep_rank0": payload,
