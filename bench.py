@@ -256,7 +256,7 @@ def extra_regimes(args, local: int, stream, mode) -> dict:
     from fluidsimulator_b200.capi import Solver
     out = {}
 
-    def run(key, scene, flagname, iterations, presteps, warm, steps, restart=False):
+    def run(key, scene, flagname, iterations, presteps, warm, steps, restart=False, stages=False):
         try:
             params, planes, state = load_scene(scene, FLAGSETS[flagname], iterations)
             n = len(state[0])
@@ -273,13 +273,21 @@ def extra_regimes(args, local: int, stream, mode) -> dict:
                         "flags": flagname, "solver_iterations": iterations,
                         "substeps": [0 if restart else presteps + warm, (0 if restart else presteps + warm) + steps],
                         "brick_path": sol.brick_status()["active"]}
+            if stages:  # per-launch time of the solver passes in this regime (CUDA events, un-graphed)
+                sol.profile_enable(True)
+                sol.profile_reset()
+                sol.step(10)
+                prof = sol.profile()
+                sol.profile_enable(False)
+                out[key]["launch_ms"] = {k: v["ms"] / v["launches"] for k, v in prof.items()
+                                         if v["launches"] and k in ("lambda", "delta", "neighbors", "xsph")}
             sol.close()
         except Exception as e:  # an extra must never take the headline down
             out[key] = {"error": str(e)[:200]}
 
     k, w = args.steps, args.warmup
     # 40 substeps from t0 (free-fall lattice; the floor impact is at substep ~82)
-    run("value_t0", args.scene, args.flags, args.iterations, 0, min(w, 10), min(k, 40))
+    run("value_t0", args.scene, args.flags, args.iterations, 0, min(w, 10), min(k, 40), stages=True)
     run("value_noflags", args.scene, "none", args.iterations, 0, min(w, 10), min(k, 40))
     run("value_allflags_3steps", args.scene, "all", args.iterations, 0, 3, 3, restart=True)
     for it in (2, 4, 8):
@@ -383,6 +391,14 @@ def run_ours(args, flags):
                     "traffic": ncu_traffic(args.scene, presteps, dom, brick["active"]), "peak_source": peak_src,
                     "alg_bytes_per_particle": ALG_BYTES[dom], "avg_launch_ms": per_launch_s * 1e3,
                     "whole_step_frac": b_alg(args.iterations, flags) * value / 1e9 / peak}
+
+    # the same fraction in the free-fall lattice regime (25 neighbours per particle instead of 30-40)
+    t0 = extras.get("value_t0", {}) if isinstance(extras, dict) else {}
+    if roofline and "launch_ms" in t0 and dom in t0["launch_ms"]:
+        a0 = ALG_BYTES[dom] * n / (t0["launch_ms"][dom] * 1e-3) / 1e9
+        roofline["t0"] = {"achieved": a0, "frac": a0 / peak, "avg_launch_ms": t0["launch_ms"][dom],
+                          "traffic": ncu_traffic(args.scene, 0, dom, brick["active"]),
+                          "whole_step_frac": b_alg(args.iterations, flags) * t0["value"] / 1e9 / peak}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

@@ -150,6 +150,7 @@ struct SlabBuffers {
   int tot_cap;              // capacity of the sorted arrays (owned + ghosts)
   int mcap;                 // migration message capacity (particles)
   int gcap;                 // ghost message capacity (particles)
+  PeerSync sync;            // exchange fused into the next consumer kernel (mine == nullptr: not fused)
 };
 // migration, one hop: particles whose predicted x-cell left the slab go into the two messages and
 // the slots they vacate are refilled from the tail of the owned range (O(migrants) data movement)

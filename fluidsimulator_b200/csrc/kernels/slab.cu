@@ -108,8 +108,9 @@ k_slab_refill(float4* __restrict__ pos_o, float4* __restrict__ pred_o, uint32_t*
 __global__ void __launch_bounds__(kThreads)
 k_slab_arrive(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pos_o,
               float4* __restrict__ pred_o, uint32_t* __restrict__ gid_o, SlabCounts* __restrict__ counts,
-              StatusBlock* st, float inv_h, int cap, int mcap, int last_hop) {
+              StatusBlock* st, float inv_h, int cap, int mcap, int last_hop, PeerSync sync) {
   pdl_wait();
+  peer_sync(sync, st);
   if (batch_failed(st)) return;
   const int cut_lo = counts->cut_lo, cut_hi = counts->cut_hi;
   if (hdr_failed(recv_l) || hdr_failed(recv_r)) {
@@ -238,8 +239,9 @@ __device__ __forceinline__ uint32_t ghost_key(float4 q, float inv_h, const GridD
 __global__ void __launch_bounds__(kThreads)
 k_slab_ghost_unpack(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ pred_s,
                     float4* __restrict__ pos_s, int2* __restrict__ cell_range, const GridDesc* __restrict__ desc,
-                    SlabCounts* __restrict__ counts, StatusBlock* st, float inv_h, int gcap, int tot_cap) {
+                    SlabCounts* __restrict__ counts, StatusBlock* st, float inv_h, int gcap, int tot_cap, PeerSync sync) {
   pdl_wait();
+  peer_sync(sync, st);
   if (batch_failed(st)) return;
   if (hdr_failed(recv_l) || hdr_failed(recv_r)) {
     st->peer_failed = 1;
@@ -280,8 +282,9 @@ k_slab_ghost_unpack(const float4* __restrict__ recv_l, const float4* __restrict_
 // (the outgoing side is HaloOut::put inside the delta / xsph kernels, kernels/solve.cu)
 __global__ void __launch_bounds__(kThreads)
 k_slab_halo_unpack(const float4* __restrict__ recv_l, const float4* __restrict__ recv_r, float4* __restrict__ arr,
-                   const SlabCounts* __restrict__ counts, const StatusBlock* st, int gcap) {
+                   const SlabCounts* __restrict__ counts, StatusBlock* st, int gcap, PeerSync sync) {
   pdl_wait();
+  peer_sync(sync, st);
   if (batch_failed(st)) return;
   const int t = blockIdx.x * kThreads + threadIdx.x;
   const int side = t / gcap, k = t - side * gcap;
@@ -360,6 +363,16 @@ k_slab_xhist(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
 
 inline int grid_for(int n) { return (n + kThreads - 1) / kThreads; }
 
+// The exchange that precedes consumer kernel `kind`, when the transport fused it (SlabBuffers::sync).
+inline PeerSync sync_for(const SlabBuffers& sb, int kind) {
+  PeerSync ps = sb.sync;
+  if (ps.mine) {
+    ps.arrivals = &sb.counts->sync_arrivals[kind];
+    ps.done = &sb.counts->sync_done[kind];
+  }
+  return ps;
+}
+
 }  // namespace
 
 // ================================================================== launchers
@@ -375,7 +388,7 @@ int launch_slab_merge(float4* pos_o, float4* pred_o, const SlabBuffers& sb, cons
                       cudaStream_t s) {
   PBF_LAUNCH(k_slab_arrive, grid_for(2 * sb.mcap), kThreads, s, sb.recv[0], sb.recv[1], pos_o, pred_o, sb.gid_o, sb.counts,
                                                           sb.status, c.inv_h, sb.cap, sb.mcap,
-                                                          last_hop ? 1 : 0);
+                                                          last_hop ? 1 : 0, sync_for(sb, 0));
   return 1;
 }
 
@@ -391,13 +404,13 @@ int launch_slab_ghost_unpack(float4* pred_s, float4* pos_s, const GridBuffers& g
                              const StepConsts& c, cudaStream_t s) {
   PBF_LAUNCH(k_slab_ghost_unpack, grid_for(2 * sb.gcap), kThreads, s, sb.recv[0], sb.recv[1], pred_s, pos_s, g.cell_range,
                                                                 g.desc, sb.counts, sb.status, c.inv_h, sb.gcap,
-                                                                sb.tot_cap);
+                                                                sb.tot_cap, sync_for(sb, 1));
   return 1;
 }
 
 int launch_slab_halo_unpack(float4* arr, const SlabBuffers& sb, cudaStream_t s) {
   PBF_LAUNCH(k_slab_halo_unpack, grid_for(2 * sb.gcap), kThreads, s, sb.recv[0], sb.recv[1], arr, sb.counts, sb.status,
-                                                               sb.gcap);
+                                                               sb.gcap, sync_for(sb, 2));
   return 1;
 }
 

@@ -62,6 +62,10 @@ struct Transport {
   virtual void abort() {}
   // a batch was replayed because a neighbour's flag timed out: wait longer next time
   virtual void relax_timeout() {}
+  // Direct-store transports between processes: instead of a flag kernel of its own, the exchange
+  // runs inside the kernel that consumes the messages (pbf::peer_sync).  Returns false when the
+  // transport has to run exchange() itself.
+  virtual bool fuse(pbf_ctx* ctx, pbf::PeerSync* sync) { (void)ctx; (void)sync; return false; }
   // true when exchange() is purely stream-ordered, i.e. may be recorded into a CUDA graph
   virtual bool capturable() const { return false; }
   // Called at the start of every slab batch attempt, before anything is enqueued: (re)establish

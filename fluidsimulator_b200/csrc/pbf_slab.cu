@@ -352,47 +352,14 @@ struct LocalTransport : Transport {
 //     message its neighbour has not unpacked yet (the neighbour's signal for exchange i+1 is only
 //     sent after it unpacked exchange i);
 //   * epochs come from a device-side counter: replaying the graph needs no patched parameters.
-struct PeerMailbox {
-  unsigned int arrived[2];  // epoch last published by the left / right neighbour
-  unsigned int epoch;       // exchanges this rank has started
-  unsigned int pad;
-};
 constexpr size_t kMailboxElems = 16;  // float4 elements reserved for the mailbox (256 B)
 
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
+// The exchange as a kernel of its own (in-process groups, where the consumer kernels of several
+// slabs share one GPU and must not spin; and PBF_SLAB_FUSED=0).
 __global__ void k_peer_signal_wait(PeerMailbox* mine, PeerMailbox* left, PeerMailbox* right, StatusBlock* st,
                                    unsigned long long timeout_ns) {
   pdl_wait();
-  // All stores of the preceding pack kernel are complete (kernel boundary); the fences order them
-  // before the flags at system scope.  Runs even when the batch has failed: a neighbour must never
-  // be left waiting.
-  const unsigned int e = mine->epoch + 1u;
-  mine->epoch = e;
-  __threadfence_system();
-  if (left) *reinterpret_cast<volatile unsigned int*>(&left->arrived[1]) = e;    // I am its right neighbour
-  if (right) *reinterpret_cast<volatile unsigned int*>(&right->arrived[0]) = e;  // I am its left neighbour
-  __threadfence_system();
-  const unsigned long long t0 = global_ns();
-  for (int side = 0; side < 2; ++side) {
-    if (!(side == 0 ? left : right)) continue;
-    const volatile unsigned int* flag = &mine->arrived[side];
-    unsigned int spins = 0;
-    while ((int)(*flag - e) < 0) {
-      // wall clock (%globaltimer), not SM cycles: the limit must not depend on the clock the GPU runs at.
-      // Never hang: a neighbour that stalled (lazy module load, graph instantiation, a profiler replay, a
-      // shared GPU) or died fails the batch with a retryable flag; slab_step restores and replays it.
-      if ((++spins & 63u) == 0 && global_ns() - t0 > timeout_ns) {
-        st->peer_timeout = 1;
-        break;
-      }
-    }
-  }
-  __threadfence_system();
+  peer_signal_wait(mine, left, right, st, timeout_ns);
 }
 
 struct PeerTransport : Transport {
@@ -422,6 +389,27 @@ struct PeerTransport : Transport {
   }
   void relax_timeout() override {
     if (timeout_ns < (1ull << 40)) timeout_ns *= 2;
+  }
+  // PBF_SLAB_FUSED=1: between processes the exchange runs inside the consumer kernel (pbf::peer_sync;
+  // one launch less per exchange, 6 per substep).  MEASURED on 2 x B200 (fluid_million, substeps
+  // 50-300, tools/gpu/r02n_fused.sh): 0.601 / 0.912 / 0.713 / 0.661 ms per substep fused against
+  // 0.592 / 0.904 / 0.705 / 0.658 with the one-thread flag kernel — the launch it saves is paid back
+  // by a whole grid (2 * gcap / 256 blocks) taking tickets and spinning, so it stays OFF.  Never
+  // inside one process: several slabs may share a GPU there, and a grid of spinning blocks could
+  // keep a neighbour's producer kernel from ever being scheduled.
+  bool fuse(pbf_ctx* ctx, PeerSync* sync) override {
+    (void)ctx;
+    static const bool enabled = [] {
+      const char* e = std::getenv("PBF_SLAB_FUSED");
+      return e && e[0] == '1';
+    }();
+    if (!active || group || !enabled) return false;
+    sync->mine = reinterpret_cast<PeerMailbox*>(win);
+    sync->left = reinterpret_cast<PeerMailbox*>(remote[0]);
+    sync->right = reinterpret_cast<PeerMailbox*>(remote[1]);
+    sync->arrivals = sync->done = nullptr;  // per consumer kernel, filled by its launcher
+    sync->timeout_ns = timeout_ns;
+    return true;
   }
 
   ~PeerTransport() override {
@@ -577,6 +565,7 @@ void slab_fill(pbf_ctx* ctx, SlabBuffers& sb) {
   sb.gid_o = sl.gid_o.p;
   sb.holes = sl.holes.p;
   sb.send[0] = sb.send[1] = sb.recv[0] = sb.recv[1] = nullptr;  // slab_bind, per exchange
+  sb.sync = PeerSync{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   sb.cut_lo = sl.cut_lo;
   sb.cut_hi = sl.cut_hi;
   sb.cap = (int)ctx->cap;
@@ -600,10 +589,16 @@ void slab_bind(pbf_ctx* ctx, SlabBuffers& sb, int index, int count) {
 // One exchange with both neighbours.
 int slab_exchange(pbf_ctx* ctx, SlabBuffers& sb, size_t elems) {
   SlabState& sl = ctx->slab;
-  stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
-  const int rc = sl.transport->exchange(ctx, sb.send, sb.recv, elems * sizeof(float4));
-  stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
-  if (rc != PBF_OK) return rc;
+  // fused: the kernel that consumes the messages (launched next, on this stream) runs the exchange
+  sb.sync = PeerSync{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  const bool side_stream = ctx->stream == sl.side;  // PBF_SLAB_OVERLAP: the consumer runs on another stream
+  if (side_stream || !sl.transport->fuse(ctx, &sb.sync)) {
+    sb.sync = PeerSync{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
+    const int rc = sl.transport->exchange(ctx, sb.send, sb.recv, elems * sizeof(float4));
+    stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
+    if (rc != PBF_OK) return rc;
+  }
   sl.exchanges++;
   sl.bytes_sent += ((sl.rank > 0) + (sl.rank + 1 < sl.nranks)) * elems * sizeof(float4);
   sl.parity ^= 1;
@@ -651,7 +646,9 @@ int slab_substep(pbf_ctx* ctx) {
     slab_bind(ctx, sb, xi++, n_ex);
     k = launch_slab_split(ctx->pos_o.p, ctx->pred_o.p, sb, c, s);
     if ((rc = slab_exchange(ctx, sb, 1 + 2 * (size_t)sl.mcap)) != PBF_OK) return rc;
+    stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);  // with a fused exchange the waiting happens in here
     k += launch_slab_merge(ctx->pos_o.p, ctx->pred_o.p, sb, c, hop == sl.hops - 1, s);
+    stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
     t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
   }
   launches += launch_grid_finalize(g, 2, n_own, s);
@@ -673,7 +670,9 @@ int slab_substep(pbf_ctx* ctx) {
   slab_bind(ctx, sb, xi++, n_ex);
   k = launch_slab_ghost_pack(g.keys[out], ctx->pred_a.p, ctx->pos_s.p, g, sb, s);
   if ((rc = slab_exchange(ctx, sb, 1 + 2 * (size_t)sl.gcap)) != PBF_OK) return rc;
+  stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
   k += launch_slab_ghost_unpack(ctx->pred_a.p, ctx->pos_s.p, g, sb, c, s);
+  stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
   t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
 
   stage_mark(ctx, PBF_STAGE_NEIGHBORS, 1);
@@ -719,7 +718,9 @@ int slab_substep(pbf_ctx* ctx) {
     if (!refresh) break;
     if (last || !overlap) {
       if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
+      stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
       k = launch_slab_halo_unpack(b.pred[cur], sb, s);
+      stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
       t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
       if (!last) {
         stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
@@ -765,7 +766,9 @@ int slab_substep(pbf_ctx* ctx) {
     if (tail_vort) {
       k = 0;
       if ((rc = slab_exchange(ctx, sb, (size_t)sl.gcap)) != PBF_OK) return rc;
+      stage_mark(ctx, PBF_STAGE_EXCHANGE, 1);
       k += launch_slab_halo_unpack(b.vel[1], sb, s);
+      stage_mark(ctx, PBF_STAGE_EXCHANGE, 0);
       t.launches[PBF_STAGE_EXCHANGE] += k; launches += k;
     }
   }
