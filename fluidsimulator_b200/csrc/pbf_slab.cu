@@ -151,17 +151,14 @@ int plan_cuts_hist(const std::vector<size_t>& hist, int lo, int nranks, float gh
 
 // Default ghost weight of every planner call of this process (environment PBF_SLAB_GHOST_WEIGHT,
 // 0 = balance owned particles only).
-float default_ghost_weight() {
-  static const float w = [] {
-    const char* e = std::getenv("PBF_SLAB_GHOST_WEIGHT");
-    if (e && *e) {
-      char* end = nullptr;
-      const float v = std::strtof(e, &end);
-      if (end != e && v >= 0.0f && v <= 1.0f) return v;
-    }
-    return 0.5f;
-  }();
-  return w;
+float default_ghost_weight() {  // read on every call: an A/B run changes it between two uploads of one process
+  const char* e = std::getenv("PBF_SLAB_GHOST_WEIGHT");
+  if (e && *e) {
+    char* end = nullptr;
+    const float v = std::strtof(e, &end);
+    if (end != e && v >= 0.0f && v <= 1.0f) return v;
+  }
+  return 0.5f;
 }
 
 int plan_cuts(size_t n, const float* px, float h, int nranks, std::vector<int>& cuts, std::string& err) {

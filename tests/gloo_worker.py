@@ -36,6 +36,12 @@ def main():
         expect[4] = expect[4] - np.float32(1.0)
         for a, b in zip(full, expect):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        # the multi-GPU bench line's parity witness hashes exactly this gathered state
+        import bench
+        assert bench.combined16(full) == bench.combined16(expect)
+        step, digest = bench.golden_digest("fluid_million", "stable", 4, "strict")
+        assert step == 65 and len(digest) == 16
+        assert bench.golden_digest("fluid_million", "stable", 2, "strict") is None   # other workloads: no digest
         print("gloo slab plumbing ok", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -8,6 +8,8 @@ Runs (tests/golden/million.json, one entry each; existing entries are kept unles
                            substeps 65 and 280
     fluid_million:all      the same scene with vorticity on, substep 3 (afterwards the reference blows up)
     block_16m:stable       the synthetic 252^3 block of the multi-GPU runs, substep 2
+    fluid_double_dem:all   BASELINE.json configs[0] (142 560 particles, all flags), substeps 40 and 80:
+                           far into the reference's own divergence (sparse cell table, K in the thousands)
 Per step: sha256 of the six state arrays, and the combined 16-hex digest tools/quick_ab.py prints
 (sha256 over the six arrays in a row), so that a digest logged by a GPU run can be compared with the
 reference without re-running either.  Kept apart from make_golden.py because of its run time."""
@@ -33,6 +35,9 @@ RUNS = {
     "fluid_million:stable": (lambda: scenes.SCENES["fluid_million"], H.STABLE_FLAGS, [65, 280]),
     "fluid_million:all": (lambda: scenes.SCENES["fluid_million"], H.ALL_FLAGS, [3]),
     "block_16m:stable": (scenes.block_16m, H.STABLE_FLAGS, [2]),
+    # BASELINE.json configs[0] (the CPU parity reference run: fluid_double_dem, all flags), deep into the
+    # reference's own vorticity blow-up (~10 000 particles in one cell by substep 80)
+    "fluid_double_dem:all": (lambda: scenes.SCENES["fluid_double_dem"], H.ALL_FLAGS, [40, 80]),
 }
 
 

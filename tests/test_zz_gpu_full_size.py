@@ -13,14 +13,15 @@ pytestmark = pytest.mark.gpu
 FLAGSETS = {"none": H.NO_FLAGS, "stable": H.STABLE_FLAGS, "all": H.ALL_FLAGS}
 
 
-@pytest.mark.parametrize("run", ["fluid_million:stable", "fluid_million:all", "block_16m:stable"])
+@pytest.mark.parametrize("run", ["fluid_million:stable", "fluid_million:all", "block_16m:stable", "fluid_double_dem:all"])
 def test_full_size_runs_match_the_reference_digests(built, run):
     """The workloads bench.py measures, at full size, against the reference itself: free-running
     state after N substeps must hash to what the unmodified reference CPU solver produced
     (tests/golden/million.json, written by tests/golden/make_golden_million.py — a 25-minute CPU
     run, so the digests are committed): BASELINE.json's fluid_million (1 000 000 particles) through
     280 substeps, the same scene with vorticity for the 3 substeps before the reference blows up,
-    and the 16 M-particle block of the multi-GPU runs."""
+    the 16 M-particle block of the multi-GPU runs, and BASELINE.json's configs[0] (fluid_double_dem,
+    all flags) 80 substeps deep into the reference's own blow-up."""
     import json
     from fluidsimulator_b200.capi import Solver
     path = G.GOLDEN / "million.json"
