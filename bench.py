@@ -281,6 +281,16 @@ def extra_regimes(args, local: int, stream, mode) -> dict:
                 sol.profile_enable(False)
                 out[key]["launch_ms"] = {k: v["ms"] / v["launches"] for k, v in prof.items()
                                          if v["launches"] and k in ("lambda", "delta", "neighbors", "xsph")}
+                # and the cuda_step contract (pinned host arrays in and out every substep) in this regime
+                import torch
+                host = [torch.from_numpy(a).pin_memory().numpy() for a in sol.download()]
+                sol.step_host(host, 1)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    sol.step_host(host, 1)
+                torch.cuda.synchronize()
+                out[key]["e2e"] = n * 10 / (time.perf_counter() - t0)
             sol.close()
         except Exception as e:  # an extra must never take the headline down
             out[key] = {"error": str(e)[:200]}
@@ -422,7 +432,9 @@ def run_ours(args, flags):
         "parity": parity,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": n * e2e_steps / e2e_s, "unit": "particle-substeps/s", "h2d_bytes_per_step": 24 * n,
-                "d2h_bytes_per_step": 24 * n, "steps": e2e_steps, "call": "pbf_step_host (cuda_step contract)"},
+                "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
+                "call": "pbf_step_host (cuda_step contract; one CUDA graph per call on pinned arrays)",
+                "value_t0": t0.get("e2e")},
         "gpu_launches": launches, "batches_replayed_in_timed_region": retried, "clocks": clocks, "stages": stages,
         "ms_per_step_profiled": ms_prof / args.steps,
         "extra": extras,

@@ -460,8 +460,13 @@ class SlabSolver(Solver):
         self._check(self.lib.pbf_slab_upload(self.ctx, arrs[0].shape[0], *[fptr(a) for a in arrs]))
 
     def slab_upload_owned(self, gid, state6):
-        gid = np.ascontiguousarray(gid, dtype=np.int64)
+        """This rank's particles from host arrays.  gid None: the same particles in the same order as
+        the last slab_download returned (positions and velocities only)."""
         arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in state6]
+        if gid is None:
+            self._check(self.lib.pbf_slab_upload_owned(self.ctx, arrs[0].shape[0], None, *[fptr(a) for a in arrs]))
+            return
+        gid = np.ascontiguousarray(gid, dtype=np.int64)
         self._check(self.lib.pbf_slab_upload_owned(self.ctx, gid.shape[0], gid.ctypes.data_as(_i64p),
                                                    *[fptr(a) for a in arrs]))
 
@@ -497,17 +502,19 @@ class SlabSolver(Solver):
     def rebalance_count(self) -> int:
         return int(self.lib.pbf_slab_rebalance_count(self.ctx))
 
-    def slab_download(self, out=None):
+    def slab_download(self, out=None, ids=True):
         """(global ids, six SoA arrays) of the owned particles.  `out` = (int64 array, six float32
-        arrays) of sufficient capacity (e.g. pinned) to receive them in place."""
+        arrays) of sufficient capacity (e.g. pinned) to receive them in place.  ids=False skips the
+        ids (returns None for them)."""
         n = self.owned()
         if out is None:
             gid = np.empty(n, dtype=np.int64)
             arrs = [np.empty(n, dtype=np.float32) for _ in range(6)]
         else:
             gid, arrs = out[0][:n], [a[:n] for a in out[1]]
-        self._check(self.lib.pbf_slab_download(self.ctx, gid.ctypes.data_as(_i64p), *[fptr(a) for a in arrs]))
-        return gid, arrs
+        self._check(self.lib.pbf_slab_download(self.ctx, gid.ctypes.data_as(_i64p) if ids else None,
+                                               *[fptr(a) for a in arrs]))
+        return (gid if ids else None), arrs
 
     def slab_stats(self) -> dict:
         ex, by = C.c_uint64(0), C.c_uint64(0)

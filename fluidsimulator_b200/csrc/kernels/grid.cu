@@ -59,10 +59,15 @@ k_unpack_state(const float4* __restrict__ pos_o, const float4* __restrict__ vel_
 // ---------------------------------------------------------------- a3 + a4 bounds
 // vel += g*dt; pred = pos + vel*dt (core.cpp:155-160), then min/max of the cell
 // coordinates.  Grid-stride so that only a few thousand warps touch the six atomics.
+__device__ void grid_finalize_body(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad, NRef nr, int allow_sparse,
+                                   int brick_cap);
+
+// finalize != 0 (one GPU): the block that delivers its bounds last also writes the table descriptor
+// of the substep (what k_grid_finalize does as a kernel of its own for slabs, after migration).
 __global__ void __launch_bounds__(kThreads)
 k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
           float4* __restrict__ pred_o, StepConsts c, StatusBlock* st, NRef nr, int do_bounds,
-          const GridDesc* __restrict__ desc, unsigned long long* __restrict__ cell_key) {
+          GridDesc* desc, unsigned long long* __restrict__ cell_key, uint32_t cell_cap, int finalize, int brick_cap) {
   pdl_wait();
   if (batch_failed(st)) return;
   const int n = nr.get();
@@ -114,6 +119,21 @@ k_predict(const float4* __restrict__ pos_o, const float4* __restrict__ vel_o,
     // plain loads first: after the first few blocks almost nobody needs the atomic
     if (blo < *(volatile int*)&st->min_cell[a]) atomicMin(&st->min_cell[a], blo);
     if (bhi > *(volatile int*)&st->max_cell[a]) atomicMax(&st->max_cell[a], bhi);
+    __threadfence();
+  }
+  if (!finalize) return;
+  // last block out: every block's bounds (and its reads of the previous substep's descriptor) are done
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&desc->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    grid_finalize_body(desc, st, cell_cap, 1, nr, 1, brick_cap);
+    desc->ticket = 0;
   }
 }
 
@@ -127,16 +147,28 @@ __global__ void k_grid_finalize(GridDesc* desc, StatusBlock* st, uint32_t cell_c
                                 int brick_cap) {
   pdl_wait();
   if (batch_failed(st)) return;
+  grid_finalize_body(desc, st, cell_cap, pad, nr, allow_sparse, brick_cap);
+}
+
+// One thread.  The bounds were accumulated with atomics (possibly by other blocks of the running
+// kernel): they are read through volatile loads, never from a stale L1 line.
+__device__ void grid_finalize_body(GridDesc* desc, StatusBlock* st, uint32_t cell_cap, int pad, NRef nr, int allow_sparse,
+                                   int brick_cap) {
   unsigned long long cells = 1;
   bool bad = false;
-  // a slab that currently owns no particle (everything migrated away) keeps a minimal table
-  const bool empty = st->min_cell[0] == INT_MAX && st->max_cell[0] == INT_MIN;
+  int mn[3], mx[3];
   for (int a = 0; a < 3; ++a) {
-    if (empty) st->min_cell[a] = st->max_cell[a] = 0;
-    const long long lo = (long long)st->min_cell[a] - pad;
-    const long long hi = (long long)st->max_cell[a] + pad;
+    mn[a] = *(volatile int*)&st->min_cell[a];
+    mx[a] = *(volatile int*)&st->max_cell[a];
+  }
+  // a slab that currently owns no particle (everything migrated away) keeps a minimal table
+  const bool empty = mn[0] == INT_MAX && mx[0] == INT_MIN;
+  for (int a = 0; a < 3; ++a) {
+    if (empty) mn[a] = mx[a] = 0;
+    const long long lo = (long long)mn[a] - pad;
+    const long long hi = (long long)mx[a] + pad;
     const long long dim = hi - lo + 1;
-    if (st->min_cell[a] == INT_MIN || st->max_cell[a] == INT_MIN || dim <= 0 || dim > 0x7fffffffLL) bad = true;
+    if (mn[a] == INT_MIN || mx[a] == INT_MIN || dim <= 0 || dim > 0x7fffffffLL) bad = true;
     desc->lo[a] = (int)lo;
     desc->hi[a] = (int)hi;
     desc->dim[a] = (int)dim;
@@ -220,49 +252,10 @@ __device__ __forceinline__ int2 sparse_lookup(const unsigned long long* __restri
 }
 
 // Two-level exclusive scan helpers: a block scans one chunk of kScanChunk entries and publishes
-// the chunk total; k_scan_chunks turns the totals into exclusive prefixes.
+// the chunk total; k_cell_ranges sums the totals of the chunks before its own.
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanChunk = kScanThreads * kScanItems;  // 2048 entries per block
-// Exclusive scan of the chunk totals, in place (one block; there are m / kScanChunk of them).
-__global__ void __launch_bounds__(1024)
-k_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nchunks) {
-  pdl_wait();
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_sh;
-  if (batch_failed(st)) return;
-  if (threadIdx.x == 0) carry_sh = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < nchunks; base += 1024) {
-    const int i = base + threadIdx.x;
-    const uint32_t v = (i < nchunks) ? chunk_total[i] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t w = warp_sums[lane];
-      uint32_t wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += t;
-      }
-      warp_sums[lane] = wi - w;
-    }
-    __syncthreads();
-    const uint32_t excl = carry_sh + warp_sums[warp] + (incl - v);
-    if (i < nchunks) chunk_total[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_sh = excl + v;
-    __syncthreads();
-  }
-}
 
 // ---------------------------------------------------------------- a5 + a6 as a counting sort
 // The key is a dense cell index, so the sort of core.cpp:173-183 plus the run-length table of
@@ -270,7 +263,7 @@ k_scan_chunks(uint32_t* __restrict__ chunk_total, const StatusBlock* st, int nch
 // place.  The reference order inside a cell is ascending particle id (core.cpp:182); atomics hand
 // out arrival slots in arbitrary order, so the last kernel ranks every particle among the (few)
 // members of its cell by id — O(occupancy) reads per particle — and writes the final slot together
-// with the gathered positions.  6 launches; the 3-pass stable radix sort + run-length table this
+// with the gathered positions.  5 launches; the 3-pass stable radix sort + run-length table this
 // replaced took 14 (same bits, 105 -> 55 us at 1 M particles).  In slab mode "particle id" is the
 // GLOBAL id (gid): the storage order of a slab's particles is then irrelevant, which is what lets
 // migration fill holes instead of re-packing the slab (kernels/slab.cu).
@@ -341,7 +334,9 @@ k_cell_scan(const uint32_t* __restrict__ cell_count, uint32_t* __restrict__ cell
   if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
 }
 
-// (start, end) of every table cell; the counters are zeroed for the next substep
+// (start, end) of every table cell; the counters are zeroed for the next substep.  One block per scan
+// chunk; the second scan level is folded in: the block sums the totals of the chunks before its own
+// (<= cell_cap / 2048 values from L2) instead of a separate one-block kernel turning them into a prefix.
 __global__ void __launch_bounds__(kThreads)
 k_cell_ranges(uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ cell_excl,
               const uint32_t* __restrict__ chunk_total, int2* __restrict__ cell_range,
@@ -349,9 +344,27 @@ k_cell_ranges(uint32_t* __restrict__ cell_count, const uint32_t* __restrict__ ce
   pdl_wait();
   if (batch_failed(st)) return;
   const uint32_t ncells = desc->ncells;
-  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
+  const uint32_t first = blockIdx.x * (uint32_t)kScanChunk;
+  if (first >= ncells) return;
+  __shared__ uint32_t warp_sums[kThreads / 32];
+  __shared__ uint32_t s_prefix;
+  uint32_t part = 0;
+  for (uint32_t k = threadIdx.x; k < blockIdx.x; k += kThreads) part += chunk_total[k];
+  part = __reduce_add_sync(0xffffffffu, part);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) sum += warp_sums[w];
+    s_prefix = sum;
+  }
+  __syncthreads();
+  const uint32_t prefix = s_prefix;
+  const uint32_t last = min(first + (uint32_t)kScanChunk, ncells);
+  for (uint32_t c = first + threadIdx.x; c < last; c += kThreads) {
     const uint32_t cnt = cell_count[c];
-    const uint32_t start = cell_excl[c] + chunk_total[c / kScanChunk];  // chunk_total is an exclusive prefix by now
+    const uint32_t start = cell_excl[c] + prefix;
     cell_range[c] = make_int2((int)start, (int)(start + cnt));
     if (cnt) cell_count[c] = 0;
   }
@@ -623,10 +636,11 @@ int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConst
   // stream at HBM speed, few enough warps that the six bound atomics stay cheap
   int blocks = grid_for(n.n, kThreads);
   if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
-  PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1, g.desc, g.cell_key);
-  if (slab) return 1;  // migrants extend the bounds; the table descriptor follows (launch_grid_finalize)
-  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1, n, 1, g.bricks ? g.brick_cap : 0);
-  return 2;
+  // one GPU: the last block also writes the table descriptor.  Slabs: migrants extend the bounds
+  // first; the descriptor follows as a kernel of its own (launch_grid_finalize)
+  PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1, g.desc, g.cell_key, g.cell_cap,
+                                      slab ? 0 : 1, g.bricks ? g.brick_cap : 0);
+  return 1;
 }
 
 int launch_grid_finalize(const GridBuffers& g, int pad, NRef n, cudaStream_t s) {
@@ -642,13 +656,12 @@ int launch_sort(const float4* pred_o, const StepConsts& c, const GridBuffers& g,
              g.desc, g.cell_key, g.status, n);
   const int nchunks = (int)((g.cell_cap + kScanChunk - 1) / kScanChunk);
   PBF_LAUNCH(k_cell_scan, nchunks, kScanThreads, s, g.cell_count, g.cell_excl, g.chunk_total, g.desc, g.status);
-  PBF_LAUNCH(k_scan_chunks, 1, 1024, s, g.chunk_total, g.status, nchunks);
-  PBF_LAUNCH(k_cell_ranges, 148 * 8, kThreads, s, g.cell_count, g.cell_excl, g.chunk_total, g.cell_range, g.desc,
-                                            g.status);
+  PBF_LAUNCH(k_cell_ranges, nchunks, kThreads, s, g.cell_count, g.cell_excl, g.chunk_total, g.cell_range, g.desc,
+                                          g.status);
   PBF_LAUNCH(k_cell_place, grid_for(n.n, kThreads), kThreads, s, g.keys[0], g.vals[0], g.cell_range, g.slot_id,
                                                            g.status, n);
   *out = 1;
-  return 5;
+  return 4;
 }
 
 int launch_cells_reorder(const float4* pred_o, const float4* pos_o, float4* pred_s, float4* pos_s,

@@ -1291,25 +1291,34 @@ int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float*
 int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, const float* px, const float* py,
                           const float* pz, const float* vx, const float* vy, const float* vz) {
   if (!ctx || !ctx->slab.enabled) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: not a slab context");
-  if (n > 0 && (!global_id || !px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: null array");
+  if (n > 0 && (!px || !py || !pz || !vx || !vy || !vz)) return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: null array");
+  // global_id == NULL: the same particles in the same order as the slab holds them now (what the last
+  // pbf_slab_download returned) — a caller that round-trips its particles through the host every
+  // substep does not have to ship and convert the ids each time
+  if (!global_id && n != ctx->n)
+    return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: without ids the count must be that of the last pbf_slab_download");
   cudaSetDevice(ctx->device);
   int rc = ensure_particles(ctx, std::max(n, ctx->cap), ctx->n);
   if (rc != PBF_OK) return rc;
   std::vector<uint32_t>& gid = ctx->slab.gid_host;
-  gid.resize(n);
-  for (size_t i = 0; i < n; ++i) {
-    if (global_id[i] < 0 || global_id[i] > 0xfffffff0ll)
-      return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: global id out of range");
-    gid[i] = (uint32_t)global_id[i];
+  if (global_id) {
+    gid.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      if (global_id[i] < 0 || global_id[i] > 0xfffffff0ll)
+        return fail(ctx, PBF_E_INVALID, "pbf_slab_upload_owned: global id out of range");
+      gid[i] = (uint32_t)global_id[i];
+    }
   }
   // A particle outside the cuts is legal input: the next substep migrates it (one hop per slab).
   if (n) {
     const float* src[6] = {px, py, pz, vx, vy, vz};
     for (int a = 0; a < 6; ++a)
       PBF_CUDA(ctx, cudaMemcpyAsync(ctx->soa[a].p, src[a], n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    PBF_CUDA(ctx, cudaMemcpyAsync(ctx->slab.gid_o.p, gid.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (global_id)
+      PBF_CUDA(ctx, cudaMemcpyAsync(ctx->slab.gid_o.p, gid.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     const float* dsoa[6] = {ctx->soa[0].p, ctx->soa[1].p, ctx->soa[2].p, ctx->soa[3].p, ctx->soa[4].p, ctx->soa[5].p};
     ctx->launch_count += launch_pack_state(dsoa, ctx->pos_o.p, ctx->vel_o.p, (int)n, ctx->stream);
+    // the host arrays may be reused on return; with ids the staging vector as well
     PBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->n = n;

@@ -1,7 +1,8 @@
-"""Multi-process driver of the x-slab decomposition: one rank per GPU (torchrun), NCCL send/recv
-between x-neighbours inside libpbf_b200.so.  torch.distributed is plumbing only:
-it ships the NCCL unique id, gathers results for checks and takes the max over ranks of the
-device-timed region.
+"""Multi-process driver of the x-slab decomposition: one rank per GPU (torchrun); halos and migrants
+move inside libpbf_b200.so by direct stores into the x-neighbours' cudaIpc windows (default) or by
+ncclSend/ncclRecv.  torch.distributed is plumbing only: it ships the NCCL unique id,
+gathers results for checks and the parity witness, and takes the max over ranks of the device-timed
+region.
 
   torchrun --nproc-per-node N -m fluidsimulator_b200.multigpu --check --scene fluid_large --steps 10
 """
@@ -17,7 +18,7 @@ import numpy as np
 from .capi import PBF_MODE_FAST, PBF_MODE_STRICT, SlabSolver, Solver, comm_unique_id, slab_plan
 
 
-# ---- host-side logic (also exercised on CPU with the gloo backend, tests/test_multigpu_host.py) ---
+# ---- host-side logic (also exercised on CPU with the gloo backend, tests/test_slab_plan.py::test_two_gloo_ranks_split_and_gather + tests/gloo_worker.py) ---
 def cell_x(px: np.ndarray, h: float) -> np.ndarray:
     """x-cell of a position: floor(x * (1.0f / h)) in float32 (reference core.cpp:28-34)."""
     inv = np.float32(1.0) / np.float32(h)
@@ -227,9 +228,12 @@ def bench(args, flags, rank: int, world: int, local: int):
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            sol.slab_upload_owned(gid, host)
+            # positions and velocities of this rank's particles in from pinned host memory, one substep,
+            # out again (the ids of the particles a rank holds are read back whenever they are needed,
+            # not shipped both ways every substep)
+            sol.slab_upload_owned(None, host)
             sol.step(1)
-            gid, host = sol.slab_download(pinned)
+            _, host = sol.slab_download(pinned, ids=False)
         barrier()
         e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -288,7 +292,7 @@ def bench(args, flags, rank: int, world: int, local: int):
         "roofline": roofline, "cpu_baseline": None,
         "e2e": {"value": n * e2e_steps / float(e2e_t.item()), "unit": "particle-substeps/s",
                 "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
-                "call": "per rank: pbf_slab_upload_owned + pbf_step(1) + pbf_slab_download"},
+                "call": "per rank: pbf_slab_upload_owned (pos, vel) + pbf_step(1) + pbf_slab_download (pos, vel)"},
         "gpu_launches": int(tot_launch.item()), "batches_replayed_in_timed_region": retried,
         "cut_replans_in_timed_region": replans, "clocks": clocks, "stages": stages,
         "stages_per_rank_ms": [{k: round(v, 4) for k, v in st.items()} for st in all_stages],

@@ -275,7 +275,8 @@ int pbf_slab_upload(pbf_ctx* ctx, size_t n_global, const float* px, const float*
                     const float* pz, const float* vx, const float* vy, const float* vz);
 /* This rank's own particles only (unique global ids, in any order): the per-rank analogue of
  * pbf_upload.  The cuts of the last pbf_slab_upload stay; particles outside them migrate during
- * the next substep. */
+ * the next substep.  global_id == NULL: the same particles, in the same order, as the last
+ * pbf_slab_download returned (n must match) — only positions and velocities are replaced. */
 int pbf_slab_upload_owned(pbf_ctx* ctx, size_t n, const int64_t* global_id, const float* px,
                           const float* py, const float* pz, const float* vx, const float* vy,
                           const float* vz);

@@ -264,3 +264,22 @@ def test_virtual_slabs_automatic_rebalancing(built):
     spread = lambda c: max(c) / (sum(c) / len(c))
     assert spread(counts["auto"][0]) < spread(counts["off"][0])
     assert spread(counts["auto"][0]) < 1.5
+
+
+def test_virtual_slabs_replan_inside_one_long_call(built):
+    """ONE pbf_step(80) call on a drifting block: the call is cut into batches of <= 25 substeps and
+    the cuts are re-planned between them (round 1 only re-planned between calls, which let the end
+    slabs of fluid_million triple during a 100-substep call).  Same bits as one GPU, the default
+    policy, no table had to grow for it twice."""
+    params, planes, state = _scene(scenes.SCENES["fluid_large"], H.STABLE_FLAGS, vx=3.0)
+    sol = _single(params, planes, state)
+    grp = SlabGroup([0] * 4, params, planes)
+    grp.upload(state)
+    grp.step(80)
+    sol.step(80)
+    _assert_same(grp, sol, "one call of 80 substeps")
+    replans = [s.rebalance_count() for s in grp.slabs]
+    assert len(set(replans)) == 1 and replans[0] >= 1, replans     # re-planned inside the single call
+    counts = grp.owned()
+    assert max(counts) / (sum(counts) / len(counts)) < 1.5
+    grp.close()
