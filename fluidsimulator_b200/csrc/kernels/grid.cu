@@ -636,11 +636,15 @@ int launch_predict(float4* pos_o, float4* vel_o, float4* pred_o, const StepConst
   // stream at HBM speed, few enough warps that the six bound atomics stay cheap
   int blocks = grid_for(n.n, kThreads);
   if (blocks > 148 * 8 * 16) blocks = 148 * 8 * 16;
-  // one GPU: the last block also writes the table descriptor.  Slabs: migrants extend the bounds
-  // first; the descriptor follows as a kernel of its own (launch_grid_finalize)
+  // The table descriptor follows as a one-thread kernel.  (Writing it from the last block of
+  // k_predict — `finalize` = 1, an atomic ticket per block — was MEASURED on B200: the predict stage
+  // went from 11.6 to 24.4 us at 1 M particles, because every block then fences its 256 pred stores
+  // before it takes the ticket; the kernel launch it saves costs 3 us.  So it stays off.)
   PBF_LAUNCH(k_predict, blocks, kThreads, s, pos_o, vel_o, pred_o, c, g.status, n, 1, g.desc, g.cell_key, g.cell_cap,
-                                      slab ? 0 : 1, g.bricks ? g.brick_cap : 0);
-  return 1;
+                                      0, 0);
+  if (slab) return 1;  // migrants extend the bounds; the table descriptor follows (launch_grid_finalize)
+  PBF_LAUNCH(k_grid_finalize, 1, 1, s, g.desc, g.status, g.cell_cap, 1, n, 1, g.bricks ? g.brick_cap : 0);
+  return 2;
 }
 
 int launch_grid_finalize(const GridBuffers& g, int pad, NRef n, cudaStream_t s) {
