@@ -842,11 +842,14 @@ bool is_pinned(const void* p) {
 // The positions of a substep are final after the last delta pass, so their 12 bytes per particle
 // cross PCIe while the tail passes still run.  The host pointers are graph parameters: the graph is
 // re-captured when the caller passes other arrays (the reference application passes the same State
-// every step).  Returns PBF_OK with *done = false when this path does not apply (pageable memory,
-// no tail pass, brick kernels, profiling, graphs off) or when the substep overflowed a device table
-// (state restored): the caller then takes the plain path, which grows the table and replays.
-int step_host_graph(pbf_ctx* ctx, size_t n, float* const host[6], bool* done) {
-  *done = false;
+// every step).  Returns PBF_OK without having stepped when this path does not apply (pageable memory,
+// no tail pass, brick kernels, profiling, graphs off: *result = kHostGraphNotUsed) or when the substep
+// overflowed a device table (kHostGraphOverflowed: the uploaded state is back in place and the caller
+// runs the plain path, which grows the table and replays).
+enum HostGraphResult { kHostGraphNotUsed = 0, kHostGraphDone = 1, kHostGraphOverflowed = 2 };
+
+int step_host_graph(pbf_ctx* ctx, size_t n, float* const host[6], HostGraphResult* result) {
+  *result = kHostGraphNotUsed;
   const StepConsts& c = ctx->consts;
   if (!ctx->use_graph || ctx->profile || ctx->slab.enabled || ctx->brick_want || n == 0) return PBF_OK;
   if (ctx->params.solver_iterations <= 0 || (!c.do_xsph && !c.do_vort)) return PBF_OK;
@@ -931,11 +934,12 @@ int step_host_graph(pbf_ctx* ctx, size_t n, float* const host[6], bool* done) {
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->pos_o.p, ctx->pos_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     PBF_CUDA(ctx, cudaMemcpyAsync(ctx->vel_o.p, ctx->vel_bak.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->tables_dirty = true;
+    *result = kHostGraphOverflowed;
     return PBF_OK;
   }
   ctx->time += ctx->params.dt;  // core.cpp:614
   ctx->last_brick = false;
-  *done = true;
+  *result = kHostGraphDone;
   return PBF_OK;
 }
 
@@ -951,11 +955,12 @@ int pbf_step_host(pbf_ctx* ctx, size_t n, float* px, float* py, float* pz, float
   int rc;
   if (nsteps == 1 && !ctx->slab.enabled && n <= 0x7fffffffu - 64) {
     float* const host[6] = {px, py, pz, vx, vy, vz};
-    bool done = false;
-    if ((rc = step_host_graph(ctx, n, host, &done)) != PBF_OK) return rc;
-    if (done) return PBF_OK;
-    if (ctx->n == n && ctx->last_status.grid_overflow + ctx->last_status.nbr_overflow + ctx->last_status.brick_overflow) {
-      // the contract graph uploaded the state and hit a table limit: replay on the plain path
+    HostGraphResult how = kHostGraphNotUsed;
+    if ((rc = step_host_graph(ctx, n, host, &how)) != PBF_OK) return rc;
+    if (how == kHostGraphDone) return PBF_OK;
+    if (how == kHostGraphOverflowed) {
+      // the contract graph uploaded the state and hit a table limit (state restored to the upload):
+      // the plain path finds the same overflow, grows the table and replays
       if ((rc = pbf_step(ctx, nsteps)) != PBF_OK) return rc;
       return pbf_download(ctx, px, py, pz, vx, vy, vz);
     }
