@@ -347,6 +347,10 @@ def run_ours(args, flags):
             sol.step(presteps - done)
         sol.step(args.warmup)
         torch.cuda.synchronize()
+        # the state the timed region starts from: the per-stage profile and the e2e loop below re-run the
+        # SAME substeps (the scene changes fast after the floor impact: substeps 125-145 cost 35 % more
+        # than 105-125)
+        start_state = state if restart else sol.download()
         sampler = ClockSampler(local)
         launches0, retried0 = sol.launch_count(), sol.batches_retried()
         sampler.start()
@@ -357,24 +361,23 @@ def run_ours(args, flags):
         nbr_total = sol.debug_sizes()[1]
         brick = sol.brick_status()
 
+        sol.upload(start_state)
         if restart:
-            sol.upload(state)
             sol.step(args.warmup)
-        # per-stage CUDA-event timing of the same K substeps' successors (profiling disables the graph)
+        # per-stage CUDA-event timing of the same K substeps (profiling disables the graph)
         sol.profile_enable(True)
         sol.profile_reset()
         ms_prof = timed_steps(sol, stream, args.steps)
         prof = sol.profile()
         sol.profile_enable(False)
 
-        # e2e: the reference-facing call (cuda_step contract): pinned host arrays in and out every step
-        if restart:
-            sol.upload(state)
-        host = [torch.from_numpy(a).pin_memory().numpy() for a in sol.download()]
+        # e2e: the reference-facing call (cuda_step contract): pinned host arrays in and out every step,
+        # over the same substeps again
+        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in start_state]
         e2e_steps = max(3, min(args.steps, 20))
         if restart:
             e2e_steps = min(e2e_steps, args.steps)
-        sol.step_host(host, 1)
+        sol.step_host(host, 1)   # captures the contract graph (untimed); the loop continues from its result
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
