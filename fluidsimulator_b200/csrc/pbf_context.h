@@ -88,6 +88,12 @@ struct SlabState {
   int mcap = 0, gcap = 0;                  // message capacities (particles)
   int hops = 1;                            // migration hops per substep
   size_t tot_cap = 0;                      // capacity of the sorted arrays (owned + ghosts)
+  // What the captured kernels COVER (grid sizes, overflow checks): <= the allocated capacities.  The
+  // allocation is generous (growing it re-allocates everything); the launch bound follows the
+  // slab's current size, so that a 16 M-particle scene does not launch twice the blocks it needs,
+  // and growing it only re-captures the graph.
+  size_t launch_own = 0;                   // owned slots covered (<= ctx->cap)
+  size_t launch_ghost = 0;                 // ghost slots covered (<= 2 * gcap); 0 = not decided yet
   size_t msg_elems = 0;                    // float4 elements per message buffer
   int parity = 0;                          // which send buffer pair the next exchange uses
   size_t n_bak = 0;                        // owned count at the start of the batch

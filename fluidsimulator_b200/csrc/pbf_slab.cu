@@ -565,8 +565,8 @@ void slab_fill(pbf_ctx* ctx, SlabBuffers& sb) {
   sb.sync = PeerSync{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   sb.cut_lo = sl.cut_lo;
   sb.cut_hi = sl.cut_hi;
-  sb.cap = (int)ctx->cap;
-  sb.tot_cap = (int)sl.tot_cap;
+  sb.cap = (int)sl.launch_own;                          // what the kernels cover, not what is allocated
+  sb.tot_cap = (int)(sl.launch_own + sl.launch_ghost);
   sb.mcap = sl.mcap;
   sb.gcap = sl.gcap;
 }
@@ -618,8 +618,8 @@ int slab_substep(pbf_ctx* ctx) {
   SlabBuffers sb{};
   slab_fill(ctx, sb);
   NeighborList nl{ctx->nbr_idx.p, ctx->nbr_count.p, ctx->K};
-  const NRef n_own = nref((int)ctx->cap, &sl.counts.p->n_own);
-  const NRef n_tot = nref((int)sl.tot_cap, &sl.counts.p->n_tot);
+  const NRef n_own = nref((int)sl.launch_own, &sl.counts.p->n_own);
+  const NRef n_tot = nref((int)(sl.launch_own + sl.launch_ghost), &sl.counts.p->n_tot);
   int launches = 0, k, rc;
   // A replayed graph bakes the send-buffer pointers in: every substep must start on the same pair.
   // (Stream-ordered transports have no write-after-read hazard on the send buffers.)
@@ -689,7 +689,7 @@ int slab_substep(pbf_ctx* ctx) {
   // a loss at 8 (2.49 vs 2.00 ms: the boundary pass with ~0.5 M ghosts competes with the interior
   // pass for the same SMs and the fork/join adds two graph edges per iteration), so it is off.
   const bool overlap = sl.overlap && sl.nranks > 1 && !ctx->profile;
-  const NRef n_interior = nref((int)ctx->cap, &sl.counts.p->n_own);
+  const NRef n_interior = nref((int)sl.launch_own, &sl.counts.p->n_own);
   const NRef n_boundary = nref(4 * sl.gcap, &sl.counts.p->n_tot);
   int cur = 0;
   stage_mark(ctx, PBF_STAGE_LAMBDA, 1);
@@ -996,6 +996,24 @@ static int slab_batch(pbf_ctx* ctx, int nsteps) {
   for (int attempt = 0; attempt < 32; ++attempt) {
     if ((rc = ensure_slab_buffers(ctx)) != PBF_OK) return bail(rc);
     if ((rc = ensure_tables(ctx)) != PBF_OK) return bail(rc);
+    {
+      // launch bounds (rank-local: they are not part of the wire format).  Owned: half above the
+      // current count (fluid_million's splash grows the end slabs of 8 by 40 % within 25 substeps;
+      // outgrowing the bound replays the batch); ghosts: everything until a batch has shown how
+      // many there are.
+      const size_t need_own = std::min(ctx->cap, n0 + n0 / 2 + 16384);
+      size_t own = sl.launch_own;
+      // (shrinking only between batches and only by a factor of three: a bound that was just grown
+      // because owned + ghosts overflowed it must survive the replay)
+      if (own < need_own || own > ctx->cap || (attempt == 0 && own > 3 * need_own)) own = need_own;
+      size_t ghost = sl.launch_ghost;
+      if (ghost == 0 || ghost > 2 * (size_t)sl.gcap) ghost = 2 * (size_t)sl.gcap;
+      if (own != sl.launch_own || ghost != sl.launch_ghost) {
+        sl.launch_own = own;
+        sl.launch_ghost = ghost;
+        invalidate_graph(ctx);
+      }
+    }
     if ((rc = sl.transport->prepare(ctx, sl.msg_elems)) != PBF_OK) return bail(rc);  // last: may end in a barrier
     if ((rc = reset_status(ctx)) != PBF_OK) return bail(rc);
     if ((rc = set_device_count(ctx, (int)n0)) != PBF_OK) return bail(rc);
@@ -1096,6 +1114,13 @@ static int slab_batch(pbf_ctx* ctx, int nsteps) {
       // layers it moves.
       // (Migration messages only grow: with direct peer stores their capacity costs memory, not
       // bandwidth, and a re-plan needs them large again a few batches later.)
+      {  // ghost slots the kernels cover: both sides, half above the largest layer pair seen (max-reduced)
+        const size_t cover = std::min<size_t>(2 * (size_t)sl.gcap, 2 * ((size_t)st.max_ghost + st.max_ghost / 2 + 1024));
+        if (cover > sl.launch_ghost || 2 * cover < sl.launch_ghost) {
+          sl.launch_ghost = cover;
+          invalidate_graph(ctx);
+        }
+      }
       const int want_g = (int)(st.max_ghost + st.max_ghost / 2 + 1024);
       if (want_g < sl.gcap / 2) {
         sl.gcap = want_g;
@@ -1133,12 +1158,24 @@ static int slab_batch(pbf_ctx* ctx, int nsteps) {
         return bail(fail(ctx, PBF_E_COMM, "pbf_step: a particle is outside every reachable slab (non-finite position?)"));
       sl.hops++;
     }
-    size_t want = ctx->cap;
-    if (st.own_overflow) want = std::max<size_t>(want, (size_t)st.max_own + st.max_own / 2 + 1024);
-    if (st.own_overflow || st.ghost_overflow) {
-      // tot_cap = cap + 2 * gcap must cover max_own (owned + ghosts)
-      ctx->cap = 0;  // force the resize below
-      if ((rc = ensure_particles(ctx, want, n0)) != PBF_OK) return bail(rc);
+    if (st.own_overflow) {
+      // max_own = the largest owned (+ ghost) count any slab saw before it stopped: a lower bound of
+      // what the batch needs.  First let the kernels cover more of what is already allocated ...
+      const size_t need = (size_t)st.max_own + st.max_own / 2 + 1024;
+      sl.launch_ghost = 2 * (size_t)sl.gcap;
+      if (need <= ctx->cap) {
+        sl.launch_own = std::max(sl.launch_own, std::min(ctx->cap, need));
+      } else {  // ... and only then re-allocate (tot_cap = cap + 2 * gcap must cover owned + ghosts)
+        ctx->cap = 0;  // force the resize
+        if ((rc = ensure_particles(ctx, need, n0)) != PBF_OK) return bail(rc);
+        sl.launch_own = ctx->cap;
+      }
+    }
+    if (st.ghost_overflow) {
+      const size_t keep_cap = ctx->cap;
+      ctx->cap = 0;  // gcap changed: the sorted arrays (cap + 2 * gcap slots) are re-sized
+      if ((rc = ensure_particles(ctx, keep_cap, n0)) != PBF_OK) return bail(rc);
+      sl.launch_ghost = 2 * (size_t)sl.gcap;
     }
     if (restore() != cudaSuccess) return bail(fail(ctx, PBF_E_CUDA, "slab batch: restoring the backup failed"));
   }
