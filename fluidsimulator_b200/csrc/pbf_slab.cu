@@ -1003,9 +1003,11 @@ static int slab_batch(pbf_ctx* ctx, int nsteps) {
       // many there are.
       const size_t need_own = std::min(ctx->cap, n0 + n0 / 2 + 16384);
       size_t own = sl.launch_own;
-      // (shrinking only between batches and only by a factor of three: a bound that was just grown
-      // because owned + ghosts overflowed it must survive the replay)
-      if (own < need_own || own > ctx->cap || (attempt == 0 && own > 3 * need_own)) own = need_own;
+      // Re-decided with hysteresis — every change re-captures the substep graph (~2 ms): up when less
+      // than an eighth of head-room is left, down only between batches and only by a factor of three
+      // (a bound that was just grown because owned + ghosts overflowed it must survive the replay).
+      const size_t low_water = std::min(ctx->cap, n0 + n0 / 8 + 4096);
+      if (own < low_water || own > ctx->cap || (attempt == 0 && own > 3 * need_own)) own = need_own;
       size_t ghost = sl.launch_ghost;
       if (ghost == 0 || ghost > 2 * (size_t)sl.gcap) ghost = 2 * (size_t)sl.gcap;
       if (own != sl.launch_own || ghost != sl.launch_ghost) {
