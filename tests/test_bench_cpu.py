@@ -49,3 +49,17 @@ def test_algorithmic_bytes_model():
     assert bench.b_alg(4, bench.FLAGSETS["all"]) == 566
     assert bench.b_alg(2, bench.FLAGSETS["all"]) == 478 and bench.b_alg(8, bench.FLAGSETS["all"]) == 742
     assert bench.ALG_BYTES["lambda"] == 16 and bench.ALG_BYTES["delta"] == 28
+
+
+def test_roofline_traffic_is_keyed_by_regime_and_kernel_family():
+    """bench.py's roofline.traffic comes from profiles/ncu_traffic.json, which
+    tools/ncu_traffic_from_summaries.py regenerates from the committed ncu summaries of the kernels
+    that ship: one figure per (scene, regime, stage, kernel family), none for what was never captured."""
+    import bench
+    t0 = bench.ncu_traffic("fluid_million", 0, "lambda", False)
+    settled = bench.ncu_traffic("fluid_million", 100, "lambda", False)
+    brick = bench.ncu_traffic("fluid_million", 0, "lambda", True)
+    assert 1.0e8 < t0 < 1.5e8 and 1.4e8 < settled < 1.8e8     # bytes per launch, 1 M particles
+    assert brick < 0.7 * t0                                   # 16-bit lists: what the brick family does save
+    assert bench.ncu_traffic("fluid_million", 100, "lambda", True) is None
+    assert bench.ncu_traffic("fluid_large", 0, "lambda", False) is None
