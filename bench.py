@@ -67,7 +67,7 @@ def ncu_traffic(scene: str, presteps: int, stage: str, brick: bool):
         table = json.loads(tf.read_text())
     except Exception:
         return None
-    regime = "t0" if presteps < 60 else "settled"
+    regime = "t0" if presteps < 60 else ("post_impact" if presteps < 160 else "settled")
     return table.get(f"{scene}:{regime}:{stage}{'_brick' if brick else ''}")
 
 

@@ -57,7 +57,9 @@ def test_roofline_traffic_is_keyed_by_regime_and_kernel_family():
     that ship: one figure per (scene, regime, stage, kernel family), none for what was never captured."""
     import bench
     t0 = bench.ncu_traffic("fluid_million", 0, "lambda", False)
-    settled = bench.ncu_traffic("fluid_million", 100, "lambda", False)
+    settled = bench.ncu_traffic("fluid_million", 200, "lambda", False)
+    impact = bench.ncu_traffic("fluid_million", 100, "lambda", False)      # the default timed regime
+    assert 1.8e8 < impact < 2.2e8
     brick = bench.ncu_traffic("fluid_million", 0, "lambda", True)
     assert 1.0e8 < t0 < 1.5e8 and 1.4e8 < settled < 1.8e8     # bytes per launch, 1 M particles
     assert brick < 0.7 * t0                                   # 16-bit lists: what the brick family does save

@@ -1,7 +1,7 @@
 """profiles/ncu_traffic.json from the COMMITTED ncu summaries (profiles/ncu_r02*.txt, written by
 tools/ncu_summary.py from `ncu --set full` captures of the kernels that ship): DRAM bytes (read +
 write) per launch, keyed "<scene>:<regime>:<stage>[_brick]" the way bench.py looks them up
-(regime t0 = capture at substep 5, settled = capture at substep 200).  Reproducible from tracked
+(regime t0 = capture at substep 5, post_impact = substep 110, settled = substep 200).  Reproducible from tracked
 files:  python tools/ncu_traffic_from_summaries.py"""
 import json
 import re
@@ -12,6 +12,7 @@ SOURCES = [  # (file, regime)
     ("ncu_r02a_shipped_r01_kernels_t0.txt", "t0"),
     ("ncu_r02a_shipped_r01_kernels_step200.txt", "settled"),
     ("ncu_r02f_lambda_delta_global_vs_persistent_brick_t0.txt", "t0"),
+    ("ncu_r02v_shipped_kernels_step110.txt", "post_impact"),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
